@@ -1,0 +1,200 @@
+/* kami_b200 -- C ABI of the B200-native self-play hot path of codeandkey/kami.
+ *
+ * Everything below runs as hand-written sm_100a CUDA kernels; there is no CPU fallback.
+ * Entry points take plain pointers and sizes.  Unless a parameter is named *_dev, pointers
+ * are HOST pointers and the call stages data itself (that is the drop-in, reference-shaped
+ * surface); *_dev pointers are device pointers for callers that keep data resident in HBM.
+ * All functions return 0 on success or a negative kb_status; kb_last_error() describes the
+ * last failure on the calling thread.
+ *
+ * Each group cites the reference interface (file:line in codeandkey/kami) it replaces.
+ * INTEGRATION.md shows the reference-side binding (kami/*.h shims in this repo).
+ */
+#ifndef KAMI_B200_H
+#define KAMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_NFEATURES 30   /* kami/env.h:19 */
+#define KB_PSIZE 4672     /* kami/env.h:20 */
+#define KB_OBSIZE 1920    /* kami/env.h:23 */
+#define KB_MAX_ACTIONS 128 /* neocortex/position.h:19 NC_MAX_PL_MOVES */
+#define KB_VALUE_WIDTH 256 /* kami/nn/nn.cpp:52 valuefc = Linear(64, 256) */
+
+typedef enum {
+    KB_OK = 0,
+    KB_ERR_CUDA = -1,       /* a CUDA call failed or no usable device */
+    KB_ERR_ARG = -2,        /* bad argument */
+    KB_ERR_STATE = -3,      /* call not valid in the current state (e.g. expand without select) */
+    KB_ERR_CAPACITY = -4,   /* node pool / path / history capacity exceeded */
+    KB_ERR_NAN = -5,        /* network output contains NaN (nn.cpp:176-180) */
+    KB_ERR_NO_CHILD = -6,   /* "no child for action" (mcts.h:129) / "no children to pick from" (:139) */
+    KB_ERR_UNSUPPORTED = -7
+} kb_status;
+
+/* Compact position, 80 bytes, the unit the encoder and tree kernels read.
+ * Replaces neocortex ncPosition (position.h:24-47, 98 656 B) on the hot path. */
+typedef struct kb_position {
+    uint64_t pieces[6];  /* occupancy by type: P N B R Q K (types.h:38-44) */
+    uint64_t white;      /* white occupancy; black = (OR pieces) ^ white */
+    uint64_t board_key;  /* xor of piece-square zobrist keys (board.c:87,106) */
+    uint64_t key;        /* position key: board ^ ep ^ castle ^ btm (position.c:301-311) */
+    uint8_t ctm;         /* 0 white, 1 black */
+    uint8_t castle;      /* WK=1 WQ=2 BK=4 BQ=8 (position.h:14-17) */
+    uint8_t ep;          /* en-passant square, 0xFF = none */
+    uint8_t hmc;         /* halfmove clock */
+    uint16_t ply;        /* Env::ply() (env.h:58) */
+    uint8_t check;       /* side to move is in check */
+    uint8_t pad;
+} kb_position;
+
+/* ---- library -------------------------------------------------------------------------- */
+int kb_init(int device);          /* bind the calling process to `device`, upload tables */
+const char* kb_last_error(void);
+int kb_device_count(void);
+int kb_device_name(char* out, int cap);
+int kb_sm_count(void);
+
+/* ---- Env: kami/env.h:41-485 ---------------------------------------------------------------
+ * A kb_env is a device-resident game: a stack of kb_position (push/pop) whose keys are the
+ * repetition history.  One warp serves one env. */
+typedef struct kb_env kb_env;
+int kb_env_create(kb_env** out);                       /* Env() env.h:52-56 */
+int kb_env_destroy(kb_env* e);
+int kb_env_reset(kb_env* e);
+int kb_env_ply(kb_env* e, int* ply);                   /* env.h:58 */
+int kb_env_push(kb_env* e, int action);                /* env.h:264-271 */
+int kb_env_pop(kb_env* e);                             /* env.h:273-279 */
+int kb_env_actions(kb_env* e, int32_t* out, int cap, int* n); /* env.h:398-423 */
+int kb_env_observe(kb_env* e, float* obs);             /* env.h:202-262, [64][30] fp32 */
+int kb_env_terminal(kb_env* e, int* terminal, float* value, int* reason); /* env.h:288-391 */
+int kb_env_encode(kb_env* e, int move, int* action);   /* env.h:60-143 */
+int kb_env_decode(kb_env* e, int action, int* move);   /* env.h:145-200 */
+int kb_env_bootstrap(kb_env* e, float window, float* out); /* env.h:476-484 */
+int kb_env_position(kb_env* e, kb_position* out);      /* current compact position */
+
+/* ---- batched position kernels (the B200 replacements of Env on many positions) ----------
+ * hist_dev/hist_len may be NULL (no repetition history). */
+int kb_encode_planes(const kb_position* pos, int n, float* obs);  /* Env::observe x n, fp32 */
+int kb_legal_actions(const kb_position* pos, int n, int32_t* actions /*[n][128]*/, int32_t* counts);
+int kb_apply_actions(kb_position* pos /*in,out*/, int n, const int32_t* actions);
+int kb_static_eval(const kb_position* pos, int n, int32_t* eval); /* ncPositionEvaluate position.c:1082 */
+/* device-resident variants used by bench.py (positions and outputs already in HBM) */
+int kb_encode_planes_dev(const kb_position* pos_dev, int n, float* obs_dev);
+int kb_encode_planes_bf16_dev(const kb_position* pos_dev, int n, void* planes_dev);
+int kb_legal_actions_dev(const kb_position* pos_dev, int n, int32_t* actions_dev, int32_t* counts_dev);
+
+/* ---- NN: kami/nn/nn.h:40-73, kami/nn/nn.cpp:26-34,59-91,155-187 -------------------------- */
+typedef struct kb_net kb_net;
+int kb_net_create(kb_net** out, int filters, int residuals);   /* NN(8,8,30,4672) nn.cpp:107 */
+int kb_net_destroy(kb_net* net);
+/* fp32 tensors in oracle/nn_oracle.py:param_order (reference register_module names) */
+size_t kb_net_blob_floats(int filters, int residuals);
+int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats);
+/* NN::infer (nn.cpp:155-187): value[i] = vh.flat[i] (the reference's memcpy of a [B,256] tensor) */
+int kb_net_infer(kb_net* net, const float* obs, int batch, float* policy, float* value);
+/* all 256 value-head outputs per position, for tolerance tests */
+int kb_net_forward_full(kb_net* net, const float* obs, int batch, float* policy, float* value256);
+/* device-resident: planes_dev is the bf16 layout kb_encode_planes_bf16_dev writes */
+int kb_net_forward_dev(kb_net* net, const void* planes_dev, int batch, float* policy_dev, float* value256_dev);
+size_t kb_net_planes_bytes(int batch);
+/* per-layer timing of the last forward (CUDA events), ms; names via kb_net_layer_name */
+int kb_net_flops(kb_net* net, double* tower_flops, double* heads_flops); /* per position */
+/* test hook: one board of an internal activation tensor as fp32 [channels][64] */
+int kb_net_debug_activation(kb_net* net, int which, int board, float* out, int* channels);
+
+/* ---- MCTS: kami/mcts.h:15-349; Selfplay::inference_main kami/selfplay.cpp:58-213 ---------- */
+typedef struct kb_tree_cfg {
+    float cpuct;                 /* mcts.h:89 */
+    int force_expand_unvisited;  /* mcts.h:90 */
+    int unvisited_node_value_pct; /* mcts.h:91 */
+    int bootstrap_weight;        /* percent, mcts.h:92 */
+    int bootstrap_window;        /* mcts.h:93 */
+    int bootstrap_amp_pct;       /* mcts.h:94 */
+    int scale_cpuct_by_actions;  /* mcts.h:95 */
+    float noise_weight;          /* mcts.h:97 */
+    uint64_t seed;               /* replaces rng.seed(time(NULL)) mcts.h:99 and rand() :173 */
+    /* self-play schedule (selfplay.cpp:16-17, 61-75) */
+    int selfplay_nodes;
+    float alpha_initial, alpha_decay, alpha_final;
+    int alpha_cutoff;
+    int draw_value_pct;
+    int value_index_mode;        /* 0 = reference (value[i] = vh.flat[i]), 1 = vh[i][0] */
+} kb_tree_cfg;
+int kb_tree_default_cfg(kb_tree_cfg* cfg);   /* the reference's in-code defaults */
+
+typedef struct kb_pool kb_pool;
+int kb_pool_create(kb_pool** out, int n_trees, int node_capacity, const kb_tree_cfg* cfg);
+int kb_pool_destroy(kb_pool* p);
+int kb_pool_size(kb_pool* p);
+
+/* single-tree API, same call protocol as kami::MCTS */
+int kb_tree_n(kb_pool* p, int tree, int* n);                       /* mcts.h:111 */
+int kb_tree_select(kb_pool* p, int tree, float* obs, int* need_eval); /* mcts.h:186-255 */
+int kb_tree_expand(kb_pool* p, int tree, const float* policy, float value, int disable_bootstrap); /* :257-327 */
+int kb_tree_pick(kb_pool* p, int tree, float alpha, double u01, int* action); /* :137-184; u01 = rand()/RAND_MAX */
+int kb_tree_push(kb_pool* p, int tree, int action);                /* :113-135 */
+int kb_tree_reset(kb_pool* p, int tree);                           /* :331-339 */
+int kb_tree_snapshot(kb_pool* p, int tree, float* pspace);         /* :341-348 */
+int kb_tree_root_children(kb_pool* p, int tree, int32_t* action, int32_t* n, float* w, float* prior, int cap, int* count);
+int kb_tree_root_w(kb_pool* p, int tree, float* w);
+int kb_tree_digest(kb_pool* p, int tree, uint64_t* digest, int64_t* count);
+int kb_tree_env(kb_pool* p, int tree, kb_position* out);           /* MCTS::get_env() root position */
+
+/* batched phases over all trees of the pool (device-resident) */
+int kb_pool_select(kb_pool* p);                 /* every tree: one leaf (terminals absorbed, moves made at budget) */
+int kb_pool_leaf_positions(kb_pool* p, kb_position* out /*[n_trees] host*/);
+int kb_pool_expand(kb_pool* p, const float* policy /*[n][4672] host*/, const float* value /*[n] host*/, int disable_bootstrap);
+int kb_pool_expand_dev(kb_pool* p, const float* policy_dev, const float* value_dev, int disable_bootstrap);
+/* the whole loop of selfplay.cpp:113-200: select -> encode -> tower+heads -> expand/backup, `iters` times */
+int kb_pool_step(kb_pool* p, kb_net* net, int iters);
+/* same, but every iteration's leaf planes round-trip through host memory like the reference
+ * (H2D of obs + D2H of policy/value inside the call); used for the end-to-end bench figure */
+int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, float* policy_host, float* value_host);
+
+typedef struct kb_pool_stats {
+    uint64_t evals;          /* NN evaluations (leaves expanded) */
+    uint64_t moves;          /* game moves played (positions) */
+    uint64_t games;          /* games finished */
+    uint64_t terminal_visits;/* simulations that ended in a terminal leaf */
+    uint64_t children_scanned; /* PUCT child records read (roofline bytes) */
+    uint64_t path_nodes;     /* nodes updated by backup */
+    uint64_t children_created;
+    uint64_t samples;        /* replay samples emitted */
+    uint64_t nodes_in_use;   /* sum over trees */
+    uint64_t kernel_launches;/* kernels this pool launched */
+} kb_pool_stats;
+int kb_pool_get_stats(kb_pool* p, kb_pool_stats* out);
+int kb_pool_reset_stats(kb_pool* p);
+/* replay sink: finished-game samples (selfplay.cpp:141-188) kept on the device as sparse rows */
+int kb_pool_drain_samples(kb_pool* p, int max_samples, float* obs /*[m][1920]*/, float* pi /*[m][4672]*/, float* z /*[m]*/, int* count);
+
+/* timing helper: elapsed ms of the last kb_pool_step / kb_net_forward_dev per phase */
+typedef struct kb_phase_ms {
+    float select, encode, tower, heads, expand, total;
+} kb_phase_ms;
+int kb_pool_last_phase_ms(kb_pool* p, kb_phase_ms* out);
+
+/* raw device memory helpers so that hosts without a CUDA runtime binding (ctypes) can keep
+ * buffers resident */
+int kb_dev_alloc(void** out, size_t bytes);
+int kb_dev_free(void* ptr);
+int kb_dev_upload(void* dst_dev, const void* src_host, size_t bytes);
+int kb_dev_download(void* dst_host, const void* src_dev, size_t bytes);
+int kb_dev_sync(void);
+int kb_host_alloc_pinned(void** out, size_t bytes);
+int kb_host_free_pinned(void* ptr);
+/* CUDA-event timer and L2 flush on the library's stream (bench.py) */
+int kb_timer_start(void);
+int kb_timer_stop(float* ms);
+int kb_flush_l2(size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAMI_B200_H */

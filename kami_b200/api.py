@@ -1,0 +1,503 @@
+"""ctypes binding of include/kami_b200.h plus Python mirrors of the reference's classes
+(kami::Env env.h:41, kami::MCTS mcts.h:66, kami::NN nn.h:40) with the same method names,
+argument meaning and error behaviour, so the parity tests read like the reference's tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PSIZE = 4672
+OBSIZE = 1920
+NFEATURES = 30
+MAX_ACTIONS = 128
+VALUE_WIDTH = 256
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# options.def.yml values of the keys the hot path reads
+DEF_YML = dict(cpuct=1.5, force_expand_unvisited=0, unvisited_node_value_pct=50, bootstrap_weight=20,
+               bootstrap_window=1600, bootstrap_amp_pct=75, scale_cpuct_by_actions=0)
+
+
+class KamiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("kami_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Position(C.Structure):
+    _fields_ = [("pieces", C.c_uint64 * 6), ("white", C.c_uint64), ("board_key", C.c_uint64), ("key", C.c_uint64),
+                ("ctm", C.c_uint8), ("castle", C.c_uint8), ("ep", C.c_uint8), ("hmc", C.c_uint8),
+                ("ply", C.c_uint16), ("check", C.c_uint8), ("pad", C.c_uint8)]
+
+
+POSITION_DTYPE = np.dtype([("pieces", "<u8", 6), ("white", "<u8"), ("board_key", "<u8"), ("key", "<u8"),
+                           ("ctm", "u1"), ("castle", "u1"), ("ep", "u1"), ("hmc", "u1"), ("ply", "<u2"),
+                           ("check", "u1"), ("pad", "u1")])
+assert POSITION_DTYPE.itemsize == 80 and C.sizeof(Position) == 80
+
+
+class TreeCfg(C.Structure):
+    _fields_ = [("cpuct", C.c_float), ("force_expand_unvisited", C.c_int), ("unvisited_node_value_pct", C.c_int),
+                ("bootstrap_weight", C.c_int), ("bootstrap_window", C.c_int), ("bootstrap_amp_pct", C.c_int),
+                ("scale_cpuct_by_actions", C.c_int), ("noise_weight", C.c_float), ("seed", C.c_uint64),
+                ("selfplay_nodes", C.c_int), ("alpha_initial", C.c_float), ("alpha_decay", C.c_float),
+                ("alpha_final", C.c_float), ("alpha_cutoff", C.c_int), ("draw_value_pct", C.c_int),
+                ("value_index_mode", C.c_int)]
+
+
+class PoolStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("evals", "moves", "games", "terminal_visits", "children_scanned",
+                                          "path_nodes", "children_created", "samples", "nodes_in_use",
+                                          "kernel_launches")]
+
+
+class PhaseMs(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("select", "encode", "tower", "heads", "expand", "total")]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libkami_b200.so")
+
+
+def build(force=False):
+    """Compile libkami_b200.so in-tree with nvcc for sm_100a (kami_b200/csrc/Makefile)."""
+    if force:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")], stdout=subprocess.DEVNULL)
+    return lib_path()
+
+
+# name -> (restype, argtypes); every symbol include/kami_b200.h declares
+_P = C.c_void_p
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_SIGS = {
+    "kb_init": (C.c_int, [C.c_int]),
+    "kb_last_error": (C.c_char_p, []),
+    "kb_device_count": (C.c_int, []),
+    "kb_device_name": (C.c_int, [C.c_char_p, C.c_int]),
+    "kb_sm_count": (C.c_int, []),
+    "kb_env_create": (C.c_int, [C.POINTER(_P)]),
+    "kb_env_destroy": (C.c_int, [_P]),
+    "kb_env_reset": (C.c_int, [_P]),
+    "kb_env_ply": (C.c_int, [_P, _i32p]),
+    "kb_env_push": (C.c_int, [_P, C.c_int]),
+    "kb_env_pop": (C.c_int, [_P]),
+    "kb_env_actions": (C.c_int, [_P, _i32p, C.c_int, _i32p]),
+    "kb_env_observe": (C.c_int, [_P, _f32p]),
+    "kb_env_terminal": (C.c_int, [_P, _i32p, _f32p, _i32p]),
+    "kb_env_encode": (C.c_int, [_P, C.c_int, _i32p]),
+    "kb_env_decode": (C.c_int, [_P, C.c_int, _i32p]),
+    "kb_env_bootstrap": (C.c_int, [_P, C.c_float, _f32p]),
+    "kb_env_position": (C.c_int, [_P, _P]),
+    "kb_encode_planes": (C.c_int, [_P, C.c_int, _f32p]),
+    "kb_legal_actions": (C.c_int, [_P, C.c_int, _i32p, _i32p]),
+    "kb_apply_actions": (C.c_int, [_P, C.c_int, _i32p]),
+    "kb_static_eval": (C.c_int, [_P, C.c_int, _i32p]),
+    "kb_encode_planes_dev": (C.c_int, [_P, C.c_int, _P]),
+    "kb_encode_planes_bf16_dev": (C.c_int, [_P, C.c_int, _P]),
+    "kb_legal_actions_dev": (C.c_int, [_P, C.c_int, _P, _P]),
+    "kb_net_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    "kb_net_destroy": (C.c_int, [_P]),
+    "kb_net_blob_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "kb_net_load_blob": (C.c_int, [_P, _f32p, C.c_size_t]),
+    "kb_net_infer": (C.c_int, [_P, _f32p, C.c_int, _f32p, _f32p]),
+    "kb_net_forward_full": (C.c_int, [_P, _f32p, C.c_int, _f32p, _f32p]),
+    "kb_net_forward_dev": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "kb_net_planes_bytes": (C.c_size_t, [C.c_int]),
+    "kb_net_flops": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "kb_net_debug_activation": (C.c_int, [_P, C.c_int, C.c_int, _f32p, _i32p]),
+    "kb_tree_default_cfg": (C.c_int, [C.POINTER(TreeCfg)]),
+    "kb_pool_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.POINTER(TreeCfg)]),
+    "kb_pool_destroy": (C.c_int, [_P]),
+    "kb_pool_size": (C.c_int, [_P]),
+    "kb_tree_n": (C.c_int, [_P, C.c_int, _i32p]),
+    "kb_tree_select": (C.c_int, [_P, C.c_int, _f32p, _i32p]),
+    "kb_tree_expand": (C.c_int, [_P, C.c_int, _f32p, C.c_float, C.c_int]),
+    "kb_tree_pick": (C.c_int, [_P, C.c_int, C.c_float, C.c_double, _i32p]),
+    "kb_tree_push": (C.c_int, [_P, C.c_int, C.c_int]),
+    "kb_tree_reset": (C.c_int, [_P, C.c_int]),
+    "kb_tree_snapshot": (C.c_int, [_P, C.c_int, _f32p]),
+    "kb_tree_root_children": (C.c_int, [_P, C.c_int, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p]),
+    "kb_tree_root_w": (C.c_int, [_P, C.c_int, _f32p]),
+    "kb_tree_digest": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "kb_tree_env": (C.c_int, [_P, C.c_int, _P]),
+    "kb_pool_select": (C.c_int, [_P]),
+    "kb_pool_leaf_positions": (C.c_int, [_P, _P]),
+    "kb_pool_expand": (C.c_int, [_P, _f32p, _f32p, C.c_int]),
+    "kb_pool_expand_dev": (C.c_int, [_P, _P, _P, C.c_int]),
+    "kb_pool_step": (C.c_int, [_P, _P, C.c_int]),
+    "kb_pool_step_hostio": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "kb_pool_get_stats": (C.c_int, [_P, C.POINTER(PoolStats)]),
+    "kb_pool_reset_stats": (C.c_int, [_P]),
+    "kb_pool_drain_samples": (C.c_int, [_P, C.c_int, _f32p, _f32p, _f32p, _i32p]),
+    "kb_pool_last_phase_ms": (C.c_int, [_P, C.POINTER(PhaseMs)]),
+    "kb_dev_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "kb_dev_free": (C.c_int, [_P]),
+    "kb_dev_upload": (C.c_int, [_P, _P, C.c_size_t]),
+    "kb_dev_download": (C.c_int, [_P, _P, C.c_size_t]),
+    "kb_dev_sync": (C.c_int, []),
+    "kb_host_alloc_pinned": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "kb_host_free_pinned": (C.c_int, [_P]),
+    "kb_timer_start": (C.c_int, []),
+    "kb_timer_stop": (C.c_int, [_f32p]),
+    "kb_flush_l2": (C.c_int, [C.c_size_t]),
+}
+ABI_SYMBOLS = tuple(sorted(_SIGS))
+
+
+def lib():
+    """Load libkami_b200.so (fails loudly when it has not been built)."""
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise KamiError(-1, "libkami_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(p)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _ck(rc):
+    if rc != 0:
+        raise KamiError(rc, lib().kb_last_error().decode(errors="replace"))
+
+
+def device_count():
+    return lib().kb_device_count()
+
+
+def init(device=-1):
+    _ck(lib().kb_init(device))
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i32p)
+
+
+def _vp(a):
+    return a.ctypes.data_as(_P)
+
+
+# ---- Env (kami/env.h) -------------------------------------------------------------------------
+class Env:
+    """Device-resident kami::Env.  Method names follow env.h."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = _P()
+        _ck(self.L.kb_env_create(C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.kb_env_destroy(self.h)
+            self.h = None
+
+    def ply(self):
+        v = C.c_int32()
+        _ck(self.L.kb_env_ply(self.h, C.byref(v)))
+        return v.value
+
+    def turn(self):
+        return 1.0 if self.ply() % 2 == 0 else -1.0
+
+    def push(self, action):
+        _ck(self.L.kb_env_push(self.h, int(action)))
+
+    def pop(self):
+        _ck(self.L.kb_env_pop(self.h))
+
+    def actions(self):
+        buf = np.zeros(MAX_ACTIONS, np.int32)
+        n = C.c_int32()
+        _ck(self.L.kb_env_actions(self.h, _ip(buf), MAX_ACTIONS, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def observe(self):
+        o = np.zeros(OBSIZE, np.float32)
+        _ck(self.L.kb_env_observe(self.h, _fp(o)))
+        return o
+
+    def terminal(self):
+        t, r, v = C.c_int32(), C.c_int32(), C.c_float()
+        _ck(self.L.kb_env_terminal(self.h, C.byref(t), C.byref(v), C.byref(r)))
+        return bool(t.value), v.value, r.value
+
+    def encode(self, move):
+        a = C.c_int32()
+        _ck(self.L.kb_env_encode(self.h, int(move), C.byref(a)))
+        return a.value
+
+    def decode(self, action):
+        m = C.c_int32()
+        _ck(self.L.kb_env_decode(self.h, int(action), C.byref(m)))
+        return m.value
+
+    def bootstrap(self, window):
+        v = C.c_float()
+        _ck(self.L.kb_env_bootstrap(self.h, float(window), C.byref(v)))
+        return v.value
+
+    bootstrap_value = bootstrap
+
+    def position(self):
+        p = np.zeros(1, POSITION_DTYPE)
+        _ck(self.L.kb_env_position(self.h, _vp(p)))
+        return p
+
+
+# ---- batched position kernels --------------------------------------------------------------------
+def as_positions(raw):
+    """[n,80] uint8 (oracle export) or structured array -> contiguous POSITION_DTYPE array."""
+    a = np.ascontiguousarray(raw)
+    if a.dtype != POSITION_DTYPE:
+        a = a.reshape(-1, 80).view(POSITION_DTYPE).reshape(-1)
+    return a
+
+
+def encode_planes(positions):
+    p = as_positions(positions)
+    out = np.zeros((len(p), OBSIZE), np.float32)
+    _ck(lib().kb_encode_planes(_vp(p), len(p), _fp(out)))
+    return out
+
+
+def legal_actions(positions):
+    p = as_positions(positions)
+    acts = np.zeros((len(p), MAX_ACTIONS), np.int32)
+    cnt = np.zeros(len(p), np.int32)
+    _ck(lib().kb_legal_actions(_vp(p), len(p), _ip(acts), _ip(cnt)))
+    return acts, cnt
+
+
+def apply_actions(positions, actions):
+    p = as_positions(positions).copy()
+    a = np.ascontiguousarray(actions, np.int32)
+    _ck(lib().kb_apply_actions(_vp(p), len(p), _ip(a)))
+    return p
+
+
+def static_eval(positions):
+    p = as_positions(positions)
+    out = np.zeros(len(p), np.int32)
+    _ck(lib().kb_static_eval(_vp(p), len(p), _ip(out)))
+    return out
+
+
+# ---- NN (kami/nn/nn.h) --------------------------------------------------------------------------
+class NN:
+    """kami::NN: NN(width, height, features, psize) with `filters` / `residuals` taken from the
+    arguments instead of the global options map (nn.cpp:42-43)."""
+
+    def __init__(self, filters=256, residuals=2, width=8, height=8, features=NFEATURES, psize=PSIZE):
+        assert (width, height, features, psize) == (8, 8, NFEATURES, PSIZE)
+        self.L = lib()
+        self.filters, self.residuals = filters, residuals
+        self.h = _P()
+        self.generation = 0
+        _ck(self.L.kb_net_create(C.byref(self.h), filters, residuals))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.kb_net_destroy(self.h)
+            self.h = None
+
+    def isCUDA(self):
+        return True
+
+    def obsize(self):
+        return OBSIZE
+
+    def polsize(self):
+        return PSIZE
+
+    def get_generation(self):
+        return self.generation
+
+    def blob_floats(self):
+        return self.L.kb_net_blob_floats(self.filters, self.residuals)
+
+    def load_blob(self, blob):
+        blob = np.ascontiguousarray(blob, np.float32)
+        _ck(self.L.kb_net_load_blob(self.h, _fp(blob), blob.size))
+
+    def infer(self, obs, batch=None):
+        """NN::infer (nn.cpp:155-187): returns (policy [B,4672], value [B]) with the reference's
+        value indexing."""
+        obs = np.ascontiguousarray(obs, np.float32)
+        B = batch or obs.size // OBSIZE
+        pol = np.zeros((B, PSIZE), np.float32)
+        val = np.zeros(B, np.float32)
+        _ck(self.L.kb_net_infer(self.h, _fp(obs), B, _fp(pol), _fp(val)))
+        return pol, val
+
+    def forward_full(self, obs):
+        obs = np.ascontiguousarray(obs, np.float32)
+        B = obs.size // OBSIZE
+        pol = np.zeros((B, PSIZE), np.float32)
+        val = np.zeros((B, VALUE_WIDTH), np.float32)
+        _ck(self.L.kb_net_forward_full(self.h, _fp(obs), B, _fp(pol), _fp(val)))
+        return pol, val
+
+    def debug_activation(self, which, board):
+        out = np.zeros((256, 64), np.float32)
+        ch = C.c_int32()
+        _ck(self.L.kb_net_debug_activation(self.h, which, board, _fp(out), C.byref(ch)))
+        return out[:ch.value].copy()
+
+    def flops(self):
+        t, h = C.c_double(), C.c_double()
+        _ck(self.L.kb_net_flops(self.h, C.byref(t), C.byref(h)))
+        return t.value, h.value
+
+
+# ---- MCTS (kami/mcts.h) ----------------------------------------------------------------------------
+def tree_cfg(**kw):
+    c = TreeCfg()
+    _ck(lib().kb_tree_default_cfg(C.byref(c)))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+class TreePool:
+    """n device-resident trees (the `MCTS trees[ibatch]` of selfplay.cpp:97)."""
+
+    def __init__(self, n_trees, node_capacity=1 << 18, cfg=None):
+        self.L = lib()
+        self.cfg = cfg or tree_cfg()
+        self.n = n_trees
+        self.h = _P()
+        _ck(self.L.kb_pool_create(C.byref(self.h), n_trees, node_capacity, C.byref(self.cfg)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.kb_pool_destroy(self.h)
+            self.h = None
+
+    def select(self):
+        _ck(self.L.kb_pool_select(self.h))
+
+    def leaf_positions(self):
+        p = np.zeros(self.n, POSITION_DTYPE)
+        _ck(self.L.kb_pool_leaf_positions(self.h, _vp(p)))
+        return p
+
+    def expand(self, policy, value, disable_bootstrap=False):
+        policy = np.ascontiguousarray(policy, np.float32)
+        value = np.ascontiguousarray(value, np.float32)
+        assert policy.size == self.n * PSIZE and value.size == self.n
+        _ck(self.L.kb_pool_expand(self.h, _fp(policy), _fp(value), int(disable_bootstrap)))
+
+    def step(self, net, iters=1):
+        _ck(self.L.kb_pool_step(self.h, net.h, iters))
+
+    def step_hostio(self, net, iters, obs, policy, value):
+        _ck(self.L.kb_pool_step_hostio(self.h, net.h, iters, _vp(obs), _vp(policy), _vp(value)))
+
+    def stats(self):
+        s = PoolStats()
+        _ck(self.L.kb_pool_get_stats(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in PoolStats._fields_}
+
+    def reset_stats(self):
+        _ck(self.L.kb_pool_reset_stats(self.h))
+
+    def phase_ms(self):
+        s = PhaseMs()
+        _ck(self.L.kb_pool_last_phase_ms(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in PhaseMs._fields_}
+
+    def drain_samples(self, max_samples):
+        obs = np.zeros((max_samples, OBSIZE), np.float32)
+        pi = np.zeros((max_samples, PSIZE), np.float32)
+        z = np.zeros(max_samples, np.float32)
+        n = C.c_int32()
+        _ck(self.L.kb_pool_drain_samples(self.h, max_samples, _fp(obs), _fp(pi), _fp(z), C.byref(n)))
+        return obs[:n.value], pi[:n.value], z[:n.value]
+
+    def tree(self, i):
+        return MCTS(pool=self, index=i)
+
+
+class MCTS:
+    """kami::MCTS call protocol (n / select / expand / pick / push / snapshot / reset) on one
+    device-resident tree."""
+
+    def __init__(self, cfg=None, pool=None, index=0, node_capacity=1 << 18):
+        self.pool = pool or TreePool(1, node_capacity, cfg)
+        self.i = index
+        self.L = self.pool.L
+        self.ph = self.pool.h
+
+    def n(self):
+        v = C.c_int32()
+        _ck(self.L.kb_tree_n(self.ph, self.i, C.byref(v)))
+        return v.value
+
+    def select(self):
+        """-> (need_eval, obs).  False means a terminal leaf was backed up (mcts.h:196-207)."""
+        o = np.zeros(OBSIZE, np.float32)
+        ne = C.c_int32()
+        _ck(self.L.kb_tree_select(self.ph, self.i, _fp(o), C.byref(ne)))
+        return bool(ne.value), o
+
+    def expand(self, policy, value, disable_bootstrap=False):
+        policy = np.ascontiguousarray(policy, np.float32)
+        assert policy.size >= PSIZE
+        _ck(self.L.kb_tree_expand(self.ph, self.i, _fp(policy), float(value), int(disable_bootstrap)))
+
+    def pick(self, alpha=0.0, u01=0.0):
+        a = C.c_int32()
+        _ck(self.L.kb_tree_pick(self.ph, self.i, float(alpha), float(u01), C.byref(a)))
+        return a.value
+
+    def push(self, action):
+        _ck(self.L.kb_tree_push(self.ph, self.i, int(action)))
+
+    def reset(self):
+        _ck(self.L.kb_tree_reset(self.ph, self.i))
+
+    def snapshot(self):
+        o = np.zeros(PSIZE, np.float32)
+        _ck(self.L.kb_tree_snapshot(self.ph, self.i, _fp(o)))
+        return o
+
+    def root_children(self):
+        a = np.zeros(256, np.int32)
+        n = np.zeros(256, np.int32)
+        w = np.zeros(256, np.float32)
+        p = np.zeros(256, np.float32)
+        k = C.c_int32()
+        _ck(self.L.kb_tree_root_children(self.ph, self.i, _ip(a), _ip(n), _fp(w), _fp(p), 256, C.byref(k)))
+        k = k.value
+        return a[:k].copy(), n[:k].copy(), w[:k].copy(), p[:k].copy()
+
+    def root_w(self):
+        v = C.c_float()
+        _ck(self.L.kb_tree_root_w(self.ph, self.i, C.byref(v)))
+        return v.value
+
+    def digest(self):
+        d, c = C.c_uint64(), C.c_int64()
+        _ck(self.L.kb_tree_digest(self.ph, self.i, C.byref(d), C.byref(c)))
+        return d.value, c.value
+
+    def root_position(self):
+        p = np.zeros(1, POSITION_DTYPE)
+        _ck(self.L.kb_tree_env(self.ph, self.i, _vp(p)))
+        return p

@@ -1,0 +1,725 @@
+// Policy/value network forward on sm_100a.
+//
+//   k_conv<N_TILE, SLICE>  implicit-GEMM 3x3 / 1x1 convolution: tcgen05.mma (bf16 x bf16 -> fp32
+//                          in TMEM), operands staged by 1-D bulk TMA copies, BN folded into
+//                          weights/bias, bias + ReLU (+ skip) fused in the TMEM epilogue.
+//   k_value_head           valueconv(1x1) + BN + ReLU + Linear(64,256) + tanh
+//   k_softmax              exp(log_softmax) over all 4672 logits
+//
+// Reference: kami/nn/nn.cpp:26-34 (residual block), :59-91 (NNModule::forward), :155-187
+// (NN::infer).  Activations use the tall-image layout of layout.cuh so that every 3x3 tap is
+// a descriptor start-address offset and no im2col copy or swizzle is needed.
+#include "net.cuh"
+
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "layout.cuh"
+#include "ptx.cuh"
+
+namespace kb {
+
+struct ConvParams {
+    const uint4* in;    // input activations, chunks_in planes per item
+    uint4* out;         // bf16 output activations (tall image) or nullptr
+    const uint4* skip;  // residual input added after the ReLU (nn.cpp:31), or nullptr
+    float* out_f32;     // dense fp32 [boards][64][n_valid] output (policy logits) or nullptr
+    const uint4* w;     // weights, one contiguous block per (pass, k-slice, tap)
+    const float* bias;  // folded bias, n_total entries
+    int items, boards;
+    int chunks_in, chunks_out;
+    int n_total;  // padded output channels (multiple of N_TILE)
+    int n_valid;  // real output channels
+    int ntaps;    // 9 (3x3, pad 1) or 1 (1x1)
+    int relu;
+};
+
+template <int N_TILE, int SLICE>
+struct ConvCfg {
+    static constexpr int MT = 4;                      // 4 M tiles x 16 tall rows = the 64 rows of an item
+    static constexpr int KSTEPS = SLICE / 2;          // one MMA covers K = 16 = two 8-channel planes
+    static constexpr int A_BYTES = SLICE * PLANE_BYTES;
+    static constexpr int B_BYTES = SLICE * N_TILE * 16;
+    static constexpr int NSTAGE = 4;
+    static constexpr int ACC_COLS = MT * N_TILE;
+    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int SMEM = BAR_BYTES + 2 * A_BYTES + NSTAGE * B_BYTES;
+    static_assert(ACC_COLS <= 512, "accumulators must fit TMEM");
+    static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert(N_TILE % 16 == 0 && N_TILE <= 256, "UMMA N for M=128");
+};
+
+template <int N_TILE, int SLICE>
+__global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
+    using C = ConvCfg<N_TILE, SLICE>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = ptx::smem_u32(smem);
+    // barrier map (8 bytes each)
+    auto b_full = [&](int s) { return bar0 + 8u * s; };
+    auto b_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto a_full = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto a_empty = [&](int s) { return bar0 + 8u * (10 + s); };
+    auto t_full = [&](int s) { return bar0 + 8u * (12 + s); };
+    auto t_empty = [&](int s) { return bar0 + 8u * (14 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    const uint32_t a_smem = bar0 + C::BAR_BYTES;
+    const uint32_t b_smem = a_smem + 2 * C::A_BYTES;
+
+    const int kslices = P.chunks_in / SLICE;
+    const int npass = P.n_total / N_TILE;
+    const int my_items = P.items > (int)blockIdx.x ? (P.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int jobs_per_item = npass * kslices;
+    const int total_jobs = my_items * jobs_per_item;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 4; ++s) {
+            ptx::mbar_init(b_full(s), 1);
+            ptx::mbar_init(b_empty(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(a_full(s), 1);
+            ptx::mbar_init(a_empty(s), 1);
+            ptx::mbar_init(t_full(s), 1);
+            ptx::mbar_init(t_empty(s), 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== producer: bulk TMA copies of activation slices (A) and weight blocks (B) =====
+        auto issue_a = [&](int job) {
+            const int ii = job / jobs_per_item, rem = job - ii * jobs_per_item;
+            const int ks = rem % kslices;
+            const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+            const int buf = job & 1;
+            ptx::mbar_wait(a_empty(buf), ((job >> 1) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(a_full(buf), C::A_BYTES);
+            const uint4* src = P.in + ((size_t)item * P.chunks_in + (size_t)ks * SLICE) * PLANE_PIX;
+            ptx::bulk_g2s(a_smem + buf * C::A_BYTES, src, C::A_BYTES, a_full(buf));
+        };
+        if (total_jobs > 0) issue_a(0);
+        int stage = 0, sphase = 0;
+        for (int job = 0; job < total_jobs; ++job) {
+            if (job + 1 < total_jobs) issue_a(job + 1);
+            const int rem = job % jobs_per_item;
+            const int pass = rem / kslices, ks = rem - pass * kslices;
+            for (int tap = 0; tap < P.ntaps; ++tap) {
+                ptx::mbar_wait(b_empty(stage), sphase ^ 1);
+                ptx::mbar_arrive_expect_tx(b_full(stage), C::B_BYTES);
+                const uint4* src = P.w + ((size_t)(pass * kslices + ks) * P.ntaps + tap) * (C::B_BYTES / 16);
+                ptx::bulk_g2s(b_smem + stage * C::B_BYTES, src, C::B_BYTES, b_full(stage));
+                if (++stage == C::NSTAGE) {
+                    stage = 0;
+                    sphase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer: one thread drives the tensor core =====
+        constexpr uint32_t idesc = ptx::idesc_bf16(128, N_TILE);
+        int stage = 0, sphase = 0, acc_count = 0;
+        for (int job = 0; job < total_jobs; ++job) {
+            const int rem = job % jobs_per_item;
+            const int ks = rem % kslices;
+            const int buf = job & 1;
+            const int acc = acc_count % C::NACC;
+            if (ks == 0) {
+                ptx::mbar_wait(t_empty(acc), ((acc_count / C::NACC) & 1) ^ 1);
+                ptx::tc_fence_after();
+            }
+            ptx::mbar_wait(a_full(buf), (job >> 1) & 1);
+            const uint32_t a_base = a_smem + buf * C::A_BYTES;
+            const uint32_t d_base = tmem_base + acc * C::ACC_COLS;
+            for (int tap = 0; tap < P.ntaps; ++tap) {
+                const int dy = P.ntaps == 9 ? tap / 3 - 1 : 0, dx = P.ntaps == 9 ? tap % 3 - 1 : 0;
+                ptx::mbar_wait(b_full(stage), sphase);
+                ptx::tc_fence_after();
+                const uint32_t b_base = b_smem + stage * C::B_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < C::KSTEPS; ++kk) {
+                    const uint64_t bdesc = ptx::smem_desc(b_base + kk * 2 * (N_TILE * 16), N_TILE * 16, 128);
+#pragma unroll
+                    for (int mt = 0; mt < C::MT; ++mt) {
+                        const int px = (16 * mt + dy) * TALL_PITCH + 1 + dx;  // may be negative for mt = 0, dy = -1
+                        const uint32_t a_addr = (uint32_t)((int)(a_base + kk * 2 * PLANE_BYTES) + px * 16);
+                        const uint64_t adesc = ptx::smem_desc(a_addr, PLANE_BYTES, TALL_PITCH * 16);
+                        const uint32_t accumulate = (ks | tap | kk) != 0;
+                        ptx::mma_bf16(d_base + mt * N_TILE, adesc, bdesc, idesc, accumulate);
+                    }
+                }
+                ptx::mma_commit(b_empty(stage));
+                if (++stage == C::NSTAGE) {
+                    stage = 0;
+                    sphase ^= 1;
+                }
+            }
+            ptx::mma_commit(a_empty(buf));
+            if (ks == kslices - 1) {
+                ptx::mma_commit(t_full(acc));
+                ++acc_count;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> bias/ReLU/skip -> bf16 (or fp32 logits) -> global =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc_count = 0;
+        for (int ii = 0; ii < my_items; ++ii) {
+            const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+            for (int pass = 0; pass < npass; ++pass, ++acc_count) {
+                const int acc = acc_count % C::NACC;
+                ptx::mbar_wait(t_full(acc), (acc_count / C::NACC) & 1);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int mt = 0; mt < C::MT; ++mt) {
+                    const int r = 32 * q + lane;          // row of the M tile == TMEM lane
+                    const int R = 16 * mt + (r >> 3);     // tall row
+                    const int x = r & 7;
+                    const int slot = (R - 1) / 9, y = (R - 1) - slot * 9;
+                    const bool valid = R >= 1 && y < 8 && slot < NB;
+                    const int px = R * TALL_PITCH + 1 + x;
+                    const int board = item * NB + slot;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * C::ACC_COLS + mt * N_TILE;
+#pragma unroll 1
+                    for (int cg = 0; cg < N_TILE / 16; ++cg) {
+                        uint32_t v[16];
+                        ptx::tmem_ld16(taddr + cg * 16, v);
+                        ptx::tmem_ld_wait();
+                        const int ch0 = pass * N_TILE + cg * 16;
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            f[j] = __uint_as_float(v[j]) + __ldg(P.bias + ch0 + j);
+                            if (P.relu) f[j] = fmaxf(f[j], 0.0f);
+                        }
+                        if (!valid) continue;
+                        if (P.out_f32) {
+                            if (board < P.boards) {
+                                float* dst = P.out_f32 + ((size_t)board * 64 + (y * 8 + x)) * P.n_valid;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (ch0 + j < P.n_valid) dst[ch0 + j] = f[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const size_t idx = ((size_t)item * P.chunks_out + (ch0 >> 3) + h) * PLANE_PIX + px;
+                                if (P.skip) {
+                                    const uint4 s4 = P.skip[idx];
+                                    const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&s4);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 sv = __bfloat1622float2(sb[k]);
+                                        f[h * 8 + 2 * k] += sv.x;
+                                        f[h * 8 + 2 * k + 1] += sv.y;
+                                    }
+                                }
+                                uint32_t w4[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 b = __floats2bfloat162_rn(f[h * 8 + 2 * k], f[h * 8 + 2 * k + 1]);
+                                    w4[k] = *reinterpret_cast<const uint32_t*>(&b);
+                                }
+                                P.out[idx] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                            }
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(t_empty(acc));
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// valueconv 1x1 (F -> 1) + BN + ReLU, Linear(64 -> 256), tanh (nn.cpp:83-88).  One block per
+// board.  wv / bv: BN-folded conv weights; fct: valuefc.weight transposed to [64][256].
+__global__ void __launch_bounds__(256) k_value_head(const uint4* x, int chunks, int boards, const float* wv, float bv, const float* fct,
+                                                     const float* fcb, float* value256, int* nan_flag) {
+    __shared__ float part[4][64];
+    __shared__ float v[64];
+    const int b = blockIdx.x;
+    if (b >= boards) return;
+    const int item = b / NB, slot = b - item * NB;
+    const int t = threadIdx.x, pix = t & 63, quarter = t >> 6;
+    const int px = tall_pixel(slot, pix);
+    float acc = 0.0f;
+    for (int c = quarter; c < chunks; c += 4) {
+        const uint4 a4 = x[((size_t)item * chunks + c) * PLANE_PIX + px];
+        const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&a4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 av = __bfloat1622float2(ab[k]);
+            acc = fmaf(av.x, wv[c * 8 + 2 * k], acc);
+            acc = fmaf(av.y, wv[c * 8 + 2 * k + 1], acc);
+        }
+    }
+    part[quarter][pix] = acc;
+    __syncthreads();
+    if (t < 64) v[t] = fmaxf(part[0][t] + part[1][t] + part[2][t] + part[3][t] + bv, 0.0f);
+    __syncthreads();
+    float o = fcb[t];
+#pragma unroll 8
+    for (int p = 0; p < 64; ++p) o = fmaf(v[p], fct[p * 256 + t], o);
+    o = tanhf(o);
+    if (o != o) atomicExch(nan_flag, 1);
+    value256[(size_t)b * 256 + t] = o;
+}
+
+// exp(log_softmax(logits)) over the 4672 actions of each board, in place (nn.cpp:80)
+__global__ void __launch_bounds__(256) k_softmax(float* logits, int boards, int* nan_flag) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const int b = blockIdx.x;
+    if (b >= boards) return;
+    float* row = logits + (size_t)b * KB_PSIZE;
+    const int t = threadIdx.x;
+    constexpr int PER = (KB_PSIZE + 255) / 256;
+    float v[PER];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int idx = t + 256 * i;
+        v[i] = idx < KB_PSIZE ? row[idx] : -INFINITY;
+        m = fmaxf(m, v[i]);
+    }
+    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((t & 31) == 0) red[t >> 5] = m;
+    __syncthreads();
+    if (t == 0) {
+        float mm = red[0];
+        for (int i = 1; i < 8; ++i) mm = fmaxf(mm, red[i]);
+        bcast = mm;
+    }
+    __syncthreads();
+    m = bcast;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        v[i] = (t + 256 * i) < KB_PSIZE ? expf(v[i] - m) : 0.0f;
+        s += v[i];
+    }
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) {
+        float ss = 0.0f;
+        for (int i = 0; i < 8; ++i) ss += red[i];
+        bcast = ss;
+    }
+    __syncthreads();
+    const float inv = 1.0f / bcast;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int idx = t + 256 * i;
+        if (idx < KB_PSIZE) {
+            const float o = v[i] * inv;
+            bad |= (o != o);
+            row[idx] = o;
+        }
+    }
+    if (bad) atomicExch(nan_flag, 1);
+}
+
+}  // namespace kb
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+using namespace kb;
+
+namespace {
+
+struct Layer {
+    int cin_chunks, slice, n_tile, n_total, n_valid, ntaps, relu;
+    uint4* w = nullptr;
+    float* bias = nullptr;
+};
+
+uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+struct kb_net {
+    int filters, residuals;
+    bool loaded = false;
+    std::vector<Layer> layers;  // conv1, (res conv1, res conv2)*, policyconv, policyconv2
+    float *wv = nullptr, *fct = nullptr, *fcb = nullptr;
+    float bv = 0.0f;
+    int cap_boards = 0;
+    uint4 *P = nullptr, *X = nullptr, *Y = nullptr, *H = nullptr;
+    int* nan_flag = nullptr;
+    // staging for the host-pointer API
+    float *obs_dev = nullptr, *pol_dev = nullptr, *val_dev = nullptr;
+    int stage_cap = 0;
+    int launches = 0;
+};
+
+namespace kb {
+
+int net_reserve(kb_net* net, int batch) {
+    if (batch <= net->cap_boards) return KB_OK;
+    cudaStreamSynchronize(main_stream());
+    cudaFree(net->P); cudaFree(net->X); cudaFree(net->Y); cudaFree(net->H);
+    const int fc = net->filters / 8;
+    KB_CUDA(cudaMalloc(&net->P, act_bytes(batch, IN_CHUNKS)));
+    KB_CUDA(cudaMalloc(&net->X, act_bytes(batch, fc)));
+    KB_CUDA(cudaMalloc(&net->Y, act_bytes(batch, fc)));
+    KB_CUDA(cudaMalloc(&net->H, act_bytes(batch, 16)));
+    // pad pixels must read as zero forever; epilogues and encoders only ever write board pixels
+    KB_CUDA(cudaMemset(net->P, 0, act_bytes(batch, IN_CHUNKS)));
+    KB_CUDA(cudaMemset(net->X, 0, act_bytes(batch, fc)));
+    KB_CUDA(cudaMemset(net->Y, 0, act_bytes(batch, fc)));
+    KB_CUDA(cudaMemset(net->H, 0, act_bytes(batch, 16)));
+    if (!net->nan_flag) {
+        KB_CUDA(cudaMalloc(&net->nan_flag, sizeof(int)));
+        KB_CUDA(cudaMemset(net->nan_flag, 0, sizeof(int)));
+    }
+    net->cap_boards = batch;
+    return KB_OK;
+}
+void* net_input_planes(kb_net* net) { return net->P; }
+int net_launches_per_forward(kb_net* net) { return (int)net->layers.size() + 2; }
+
+template <int N_TILE, int SLICE>
+static int launch_conv(const ConvParams& p, cudaStream_t st) {
+    using C = ConvCfg<N_TILE, SLICE>;
+    static bool configured = false;
+    if (!configured) {
+        KB_CUDA(cudaFuncSetAttribute(k_conv<N_TILE, SLICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        configured = true;
+    }
+    const int grid = p.items < sm_count() ? p.items : sm_count();
+    k_conv<N_TILE, SLICE><<<grid, 256, C::SMEM, st>>>(p);
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+static int run_conv(const Layer& L, const uint4* in, uint4* out, const uint4* skip, float* out_f32, int boards, cudaStream_t st) {
+    ConvParams p;
+    p.in = in;
+    p.out = out;
+    p.skip = skip;
+    p.out_f32 = out_f32;
+    p.w = L.w;
+    p.bias = L.bias;
+    p.items = items_for(boards);
+    p.boards = boards;
+    p.chunks_in = L.cin_chunks;
+    p.chunks_out = L.n_total / 8;
+    p.n_total = L.n_total;
+    p.n_valid = L.n_valid;
+    p.ntaps = L.ntaps;
+    p.relu = L.relu;
+    if (L.n_tile == 64 && L.slice == 4) return launch_conv<64, 4>(p, st);
+    if (L.n_tile == 64 && L.slice == 8) return launch_conv<64, 8>(p, st);
+    if (L.n_tile == 128 && L.slice == 4) return launch_conv<128, 4>(p, st);
+    if (L.n_tile == 128 && L.slice == 8) return launch_conv<128, 8>(p, st);
+    if (L.n_tile == 80 && L.slice == 8) return launch_conv<80, 8>(p, st);
+    set_error("no conv kernel for n_tile=%d slice=%d", L.n_tile, L.slice);
+    return KB_ERR_UNSUPPORTED;
+}
+
+int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, cudaStream_t st) {
+    if (!net->loaded) {
+        set_error("network weights not loaded");
+        return KB_ERR_STATE;
+    }
+    int r = net_reserve(net, batch);
+    if (r) return r;
+    const uint4* in = reinterpret_cast<const uint4*>(planes);
+    size_t li = 0;
+    if ((r = run_conv(net->layers[li++], in, net->X, nullptr, nullptr, batch, st))) return r;
+    for (int i = 0; i < net->residuals; ++i) {
+        if ((r = run_conv(net->layers[li++], net->X, net->Y, nullptr, nullptr, batch, st))) return r;
+        if ((r = run_conv(net->layers[li++], net->Y, net->X, net->X, nullptr, batch, st))) return r;  // x = skip + relu(...)
+    }
+    if ((r = run_conv(net->layers[li++], net->X, net->H, nullptr, nullptr, batch, st))) return r;
+    if ((r = run_conv(net->layers[li++], net->H, nullptr, nullptr, policy_dev, batch, st))) return r;
+    k_softmax<<<batch, 256, 0, st>>>(policy_dev, batch, net->nan_flag);
+    KB_CUDA(cudaGetLastError());
+    k_value_head<<<batch, 256, 0, st>>>(net->X, net->filters / 8, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, net->nan_flag);
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+}  // namespace kb
+
+namespace {
+
+struct BlobCursor {
+    const float* p;
+    size_t left;
+    const float* take(size_t n) {
+        if (n > left) return nullptr;
+        const float* r = p;
+        p += n;
+        left -= n;
+        return r;
+    }
+};
+
+// BN (eval, eps 1e-5, nn.cpp:116) folded into the preceding conv: w' = w*s, b' = (b-mean)*s + beta
+void fold_bn(const float* g, const float* beta, const float* mean, const float* var, int c, std::vector<float>& scale, std::vector<float>& shift) {
+    scale.resize(c);
+    shift.resize(c);
+    for (int i = 0; i < c; ++i) {
+        const float s = g[i] / sqrtf(var[i] + 1e-5f);
+        scale[i] = s;
+        shift[i] = beta[i] - mean[i] * s;
+    }
+}
+
+// Packs conv weights [O][Cin][k][k] (scaled per output channel) into the kernel's B layout:
+// blocks ordered (pass, k-slice, tap), each block [chunk in slice][n in tile][8 channels] bf16.
+int pack_conv(Layer& L, const float* w, const float* b, int O, int Cin, int k, const std::vector<float>* scale, const std::vector<float>* shift) {
+    const int kslices = L.cin_chunks / L.slice, npass = L.n_total / L.n_tile, taps = k * k;
+    const size_t block = (size_t)L.slice * L.n_tile * 8;
+    std::vector<uint16_t> packed((size_t)npass * kslices * taps * block, 0);
+    for (int pass = 0; pass < npass; ++pass)
+        for (int ks = 0; ks < kslices; ++ks)
+            for (int tap = 0; tap < taps; ++tap) {
+                uint16_t* dst = packed.data() + ((size_t)(pass * kslices + ks) * taps + tap) * block;
+                for (int c = 0; c < L.slice; ++c)
+                    for (int n = 0; n < L.n_tile; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int o = pass * L.n_tile + n, ci = (ks * L.slice + c) * 8 + e;
+                            float v = 0.0f;
+                            if (o < O && ci < Cin) {
+                                v = w[((size_t)o * Cin + ci) * taps + tap];
+                                if (scale) v *= (*scale)[o];
+                            }
+                            dst[((size_t)c * L.n_tile + n) * 8 + e] = f2bf(v);
+                        }
+            }
+    std::vector<float> bias(L.n_total, 0.0f);
+    for (int o = 0; o < O; ++o) bias[o] = scale ? b[o] * (*scale)[o] + (*shift)[o] : b[o];
+    KB_CUDA(cudaMalloc(&L.w, packed.size() * 2));
+    KB_CUDA(cudaMemcpy(L.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    KB_CUDA(cudaMalloc(&L.bias, bias.size() * 4));
+    KB_CUDA(cudaMemcpy(L.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    return KB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kb_net_create(kb_net** out, int filters, int residuals) {
+    KB_REQUIRE_INIT();
+    KB_ARG(out, "out");
+    KB_ARG(filters == 64 || filters == 128 || filters == 256, "filters must be 64, 128 or 256");
+    KB_ARG(residuals >= 0 && residuals <= 64, "residuals in [0, 64]");
+    kb_net* n = new (std::nothrow) kb_net();
+    if (!n) return KB_ERR_ARG;
+    n->filters = filters;
+    n->residuals = residuals;
+    *out = n;
+    return KB_OK;
+}
+
+int kb_net_destroy(kb_net* n) {
+    if (!n) return KB_OK;
+    cudaStreamSynchronize(main_stream());
+    for (auto& L : n->layers) {
+        cudaFree(L.w);
+        cudaFree(L.bias);
+    }
+    cudaFree(n->wv); cudaFree(n->fct); cudaFree(n->fcb);
+    cudaFree(n->P); cudaFree(n->X); cudaFree(n->Y); cudaFree(n->H);
+    cudaFree(n->nan_flag); cudaFree(n->obs_dev); cudaFree(n->pol_dev); cudaFree(n->val_dev);
+    delete n;
+    return KB_OK;
+}
+
+size_t kb_net_blob_floats(int F, int R) {
+    size_t conv1 = (size_t)F * 30 * 9 + F + 4 * F;
+    size_t res = 2 * ((size_t)F * F * 9 + F + 4 * F);
+    size_t pol = (size_t)128 * F + 128 + 4 * 128 + (size_t)73 * 128 + 73;
+    size_t val = (size_t)F + 1 + 4 + 256 * 64 + 256;
+    return conv1 + R * res + pol + val;
+}
+
+// Blob order = oracle/nn_oracle.py:param_order (reference module names, nn.cpp:20-23, 45-56).
+int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
+    KB_REQUIRE_INIT();
+    KB_ARG(net && blob, "net/blob");
+    const int F = net->filters, R = net->residuals;
+    if (n_floats != kb_net_blob_floats(F, R)) {
+        set_error("weight blob has %zu floats, expected %zu for filters=%d residuals=%d", n_floats, kb_net_blob_floats(F, R), F, R);
+        return KB_ERR_ARG;
+    }
+    cudaStreamSynchronize(main_stream());
+    for (auto& L : net->layers) {
+        cudaFree(L.w);
+        cudaFree(L.bias);
+    }
+    net->layers.clear();
+    BlobCursor c{blob, n_floats};
+    std::vector<float> sc, sh;
+    const int ntile = F == 64 ? 64 : 128;
+    auto conv_bn = [&](int O, int Cin, int k, int cin_chunks, int slice, int n_tile, int n_total, int relu, bool has_bn) -> int {
+        const float* w = c.take((size_t)O * Cin * k * k);
+        const float* b = c.take(O);
+        Layer L;
+        L.cin_chunks = cin_chunks;
+        L.slice = slice;
+        L.n_tile = n_tile;
+        L.n_total = n_total;
+        L.n_valid = O;
+        L.ntaps = k * k;
+        L.relu = relu;
+        int r;
+        if (has_bn) {
+            const float *g = c.take(O), *beta = c.take(O), *mean = c.take(O), *var = c.take(O);
+            fold_bn(g, beta, mean, var, O, sc, sh);
+            r = pack_conv(L, w, b, O, Cin, k, &sc, &sh);
+        } else
+            r = pack_conv(L, w, b, O, Cin, k, nullptr, nullptr);
+        if (r) return r;
+        net->layers.push_back(L);
+        return KB_OK;
+    };
+    int r;
+    if ((r = conv_bn(F, 30, 3, IN_CHUNKS, 4, ntile, F, 1, true))) return r;              // conv1 + batchnorm1 + relu
+    for (int i = 0; i < R; ++i) {
+        if ((r = conv_bn(F, F, 3, F / 8, 8, ntile, F, 1, true))) return r;              // residual conv1 + bn1 + relu
+        if ((r = conv_bn(F, F, 3, F / 8, 8, ntile, F, 1, true))) return r;              // residual conv2 + bn2 + relu (+ skip)
+    }
+    if ((r = conv_bn(128, F, 1, F / 8, 8, 128, 128, 1, true))) return r;                  // policyconv + pbatchnorm + relu
+    if ((r = conv_bn(73, 128, 1, 16, 8, 80, 80, 0, false))) return r;                     // policyconv2 (logits)
+    {   // value head
+        const float* w = c.take(F);
+        const float* b = c.take(1);
+        const float *g = c.take(1), *beta = c.take(1), *mean = c.take(1), *var = c.take(1);
+        const float* fw = c.take(256 * 64);
+        const float* fb = c.take(256);
+        const float s = g[0] / sqrtf(var[0] + 1e-5f);
+        std::vector<float> wv(F), fct(64 * 256);
+        for (int i = 0; i < F; ++i) wv[i] = w[i] * s;
+        net->bv = (b[0] - mean[0]) * s + beta[0];
+        for (int j = 0; j < 256; ++j)
+            for (int p = 0; p < 64; ++p) fct[p * 256 + j] = fw[j * 64 + p];
+        cudaFree(net->wv); cudaFree(net->fct); cudaFree(net->fcb);
+        KB_CUDA(cudaMalloc(&net->wv, F * 4));
+        KB_CUDA(cudaMalloc(&net->fct, 64 * 256 * 4));
+        KB_CUDA(cudaMalloc(&net->fcb, 256 * 4));
+        KB_CUDA(cudaMemcpy(net->wv, wv.data(), F * 4, cudaMemcpyHostToDevice));
+        KB_CUDA(cudaMemcpy(net->fct, fct.data(), 64 * 256 * 4, cudaMemcpyHostToDevice));
+        KB_CUDA(cudaMemcpy(net->fcb, fb, 256 * 4, cudaMemcpyHostToDevice));
+    }
+    net->loaded = true;
+    return KB_OK;
+}
+
+size_t kb_net_planes_bytes(int batch) { return act_bytes(batch, IN_CHUNKS); }
+
+int kb_net_forward_dev(kb_net* net, const void* planes_dev, int batch, float* policy_dev, float* value256_dev) {
+    KB_REQUIRE_INIT();
+    KB_ARG(net && planes_dev && policy_dev && value256_dev && batch > 0, "net/planes/policy/value/batch");
+    return net_forward_async(net, planes_dev, batch, policy_dev, value256_dev, main_stream());
+}
+
+static int net_stage(kb_net* net, int batch) {
+    if (batch <= net->stage_cap) return KB_OK;
+    cudaStreamSynchronize(main_stream());
+    cudaFree(net->obs_dev); cudaFree(net->pol_dev); cudaFree(net->val_dev);
+    KB_CUDA(cudaMalloc(&net->obs_dev, sizeof(float) * KB_OBSIZE * (size_t)batch));
+    KB_CUDA(cudaMalloc(&net->pol_dev, sizeof(float) * KB_PSIZE * (size_t)batch));
+    KB_CUDA(cudaMalloc(&net->val_dev, sizeof(float) * KB_VALUE_WIDTH * (size_t)batch));
+    net->stage_cap = batch;
+    return KB_OK;
+}
+
+int kb_net_forward_full(kb_net* net, const float* obs, int batch, float* policy, float* value256) {
+    KB_REQUIRE_INIT();
+    KB_ARG(net && obs && batch > 0, "net/obs/batch");
+    int r;
+    if ((r = net_stage(net, batch)) || (r = net_reserve(net, batch))) return r;
+    cudaStream_t st = main_stream();
+    KB_CUDA(cudaMemcpyAsync(net->obs_dev, obs, sizeof(float) * KB_OBSIZE * (size_t)batch, cudaMemcpyHostToDevice, st));
+    if ((r = obs_to_tall_launch(net->obs_dev, batch, net->P, st))) return r;
+    if ((r = net_forward_async(net, net->P, batch, net->pol_dev, net->val_dev, st))) return r;
+    if (policy) KB_CUDA(cudaMemcpyAsync(policy, net->pol_dev, sizeof(float) * KB_PSIZE * (size_t)batch, cudaMemcpyDeviceToHost, st));
+    if (value256) KB_CUDA(cudaMemcpyAsync(value256, net->val_dev, sizeof(float) * KB_VALUE_WIDTH * (size_t)batch, cudaMemcpyDeviceToHost, st));
+    int flag = 0;
+    KB_CUDA(cudaMemcpyAsync(&flag, net->nan_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KB_CUDA(cudaStreamSynchronize(st));
+    if (flag) {
+        int zero = 0;
+        cudaMemcpy(net->nan_flag, &zero, sizeof(int), cudaMemcpyHostToDevice);
+        set_error("inference output contains NaN");
+        return KB_ERR_NAN;
+    }
+    return KB_OK;
+}
+
+// NN::infer (nn.cpp:155-187).  The reference copies the first `batch` floats of its [batch,256]
+// value tensor, i.e. value[i] = vh[i / 256][i % 256]; reproduced bit for bit.
+int kb_net_infer(kb_net* net, const float* obs, int batch, float* policy, float* value) {
+    KB_ARG(value && policy, "policy/value");
+    int r = kb_net_forward_full(net, obs, batch, policy, nullptr);
+    if (r) return r;
+    KB_CUDA(cudaMemcpy(value, net->val_dev, sizeof(float) * (size_t)batch, cudaMemcpyDeviceToHost));
+    return KB_OK;
+}
+
+// Test hook: download one board of an internal activation tensor as fp32 [channels][64].
+// which: 0 input planes (32 ch), 1 tower output X, 2 residual scratch Y, 3 policy hidden H (128 ch).
+int kb_net_debug_activation(kb_net* net, int which, int board, float* out, int* channels) {
+    KB_REQUIRE_INIT();
+    KB_ARG(net && out && channels && board >= 0 && board < net->cap_boards, "net/out/board");
+    const uint4* buf = which == 0 ? net->P : which == 1 ? net->X : which == 2 ? net->Y : net->H;
+    const int chunks = which == 0 ? IN_CHUNKS : which == 3 ? 16 : net->filters / 8;
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
+    const int item = board / NB, slot = board % NB;
+    std::vector<uint16_t> plane((size_t)PLANE_PIX * 8);
+    for (int c = 0; c < chunks; ++c) {
+        KB_CUDA(cudaMemcpy(plane.data(), buf + ((size_t)item * chunks + c) * PLANE_PIX, PLANE_BYTES, cudaMemcpyDeviceToHost));
+        for (int q = 0; q < 64; ++q)
+            for (int e = 0; e < 8; ++e) {
+                uint32_t u = (uint32_t)plane[(size_t)tall_pixel(slot, q) * 8 + e] << 16;
+                float f;
+                memcpy(&f, &u, 4);
+                out[(size_t)(c * 8 + e) * 64 + q] = f;
+            }
+    }
+    *channels = chunks * 8;
+    return KB_OK;
+}
+
+int kb_net_flops(kb_net* net, double* tower, double* heads) {
+    KB_ARG(net, "net");
+    const double F = net->filters, R = net->residuals;
+    if (tower) *tower = 2.0 * 64 * (9 * 30) * F + R * 2.0 * (2.0 * 64 * 9 * F * F);
+    if (heads) *heads = 2.0 * 64 * F * 128 + 2.0 * 64 * 128 * 73 + 2.0 * 64 * F + 2.0 * 64 * 256;
+    return KB_OK;
+}
+
+}  // extern "C"

@@ -376,3 +376,108 @@ def uci(mv):
     if p < 6:
         r += "pnbrqk"[p]
     return r
+
+
+# ---- reference NN (LibTorch) ---------------------------------------------------------------
+_refnn = None
+
+
+def ref_nn_lib():
+    global _refnn
+    if _refnn is None:
+        p = ref_nn_path()
+        if not os.path.exists(p):
+            return None
+        L = C.CDLL(p)
+        L.ref_nn_new.restype = C.c_void_p
+        L.ref_nn_new.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int]
+        L.ref_nn_free.argtypes = [C.c_void_p]
+        L.ref_nn_is_cuda.argtypes = [C.c_void_p]
+        L.ref_nn_infer.argtypes = [C.c_void_p, c_float_p, C.c_int, c_float_p, c_float_p]
+        L.ref_nn_forward_full.argtypes = [C.c_void_p, c_float_p, C.c_int, c_float_p, c_float_p]
+        L.ref_nn_num_tensors.argtypes = [C.c_void_p]
+        L.ref_nn_tensor_info.restype = C.c_long
+        L.ref_nn_tensor_info.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_long), c_int_p, c_int_p]
+        L.ref_nn_tensor_get.argtypes = [C.c_void_p, C.c_int, c_float_p]
+        L.ref_nn_tensor_set.argtypes = [C.c_void_p, C.c_int, c_float_p]
+        L.ref_nn_set_threads.argtypes = [C.c_int]
+        _refnn = L
+    return _refnn
+
+
+class RefNN:
+    """The unmodified reference kami::NN (kami/nn/nn.cpp) on LibTorch."""
+
+    def __init__(self, filters, residuals, seed=1, force_cpu=True):
+        self.L = ref_nn_lib()
+        self.filters, self.residuals = filters, residuals
+        self.h = self.L.ref_nn_new(filters, residuals, seed, int(force_cpu))
+        self.index = {}
+        for i in range(self.L.ref_nn_num_tensors(self.h)):
+            name = C.create_string_buffer(128)
+            dims = (C.c_long * 4)()
+            rank, isint = C.c_int(), C.c_int()
+            self.L.ref_nn_tensor_info(self.h, i, name, 128, dims, C.byref(rank), C.byref(isint))
+            self.index[name.value.decode()] = (i, tuple(dims[:rank.value]), bool(isint.value))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_nn_free(self.h)
+            self.h = None
+
+    def is_cuda(self):
+        return bool(self.L.ref_nn_is_cuda(self.h))
+
+    def get_params(self):
+        out = {}
+        for name, (i, shape, isint) in self.index.items():
+            if isint:
+                continue
+            a = np.zeros(shape, np.float32)
+            self.L.ref_nn_tensor_get(self.h, i, _fp(a))
+            out[name] = a
+        return out
+
+    def set_params(self, params):
+        for name, v in params.items():
+            i, shape, isint = self.index[name]
+            a = np.ascontiguousarray(v, np.float32).reshape(shape)
+            self.L.ref_nn_tensor_set(self.h, i, _fp(a))
+
+    def infer(self, obs):
+        obs = np.ascontiguousarray(obs, np.float32)
+        B = obs.size // OBSIZE
+        pol = np.zeros((B, PSIZE), np.float32)
+        val = np.zeros(B, np.float32)
+        rc = self.L.ref_nn_infer(self.h, _fp(obs), B, _fp(pol), _fp(val))
+        if rc != 0:
+            raise RuntimeError("reference NN::infer threw")
+        return pol, val
+
+    def forward_full(self, obs):
+        obs = np.ascontiguousarray(obs, np.float32)
+        B = obs.size // OBSIZE
+        pol = np.zeros((B, PSIZE), np.float32)
+        val = np.zeros((B, 256), np.float32)
+        self.L.ref_nn_forward_full(self.h, _fp(obs), B, _fp(pol), _fp(val))
+        return pol, val
+
+
+def sample_positions(n, seed=0, max_ply=120):
+    """Synthetic positions as SURVEY.md 8(d) config 2 describes: seeded random legal games
+    sampled at plies uniform in [0, max_ply].  Returns a list of OracleEnv."""
+    rng = np.random.RandomState(seed)
+    out = []
+    while len(out) < n:
+        e = OracleEnv()
+        target = int(rng.randint(0, max_ply + 1))
+        ok = True
+        for _ in range(target):
+            if e.terminal()[0]:
+                ok = False
+                break
+            a = e.actions()
+            e.push(int(a[rng.randint(len(a))]))
+        if ok and not e.terminal()[0]:
+            out.append(e)
+    return out

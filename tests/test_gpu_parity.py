@@ -1,0 +1,337 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs and against the committed golden fixtures.  Bit-exact for planes / legality / eval /
+visit counts; stated tolerances for the bf16 network."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+import nn_oracle as NO
+from golden.make_golden import MCTS_CASES, mcts_stream
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- Env / encoder / legality -------------------------------------------------------------------
+def test_env_random_games_bit_exact(kb):
+    rng = np.random.RandomState(3)
+    for g in range(3):
+        d, o = kb.Env(), H.OracleEnv()
+        for ply in range(400):
+            td, to = d.terminal(), o.terminal()
+            assert td == to, (g, ply, td, to)
+            assert np.array_equal(d.observe(), o.observe())
+            assert np.array_equal(d.position().view(np.uint8).reshape(-1), o.export())
+            if to[0]:
+                break
+            ad, ao = d.actions(), o.actions()
+            assert np.array_equal(ad, ao), (g, ply, ad, ao)
+            assert d.bootstrap(1600.0) == o.bootstrap(1600.0)
+            a = int(ao[rng.randint(len(ao))])
+            assert d.decode(a) == o.decode(a) and d.encode(o.decode(a)) == a
+            d.push(a)
+            o.push(a)
+            if ply % 37 == 5:
+                d.pop(); o.pop(); d.push(a); o.push(a)
+
+
+def test_encoding_game_golden(kb):
+    """The reference's own deterministic test (test/encoding.cpp) replayed on the device."""
+    g = json.load(open(os.path.join(G, "encoding_game.json")))
+    e = kb.Env()
+    for a, mv in zip(g["actions"], g["moves"]):
+        acts = e.actions()
+        assert a in acts
+        assert H.uci(e.decode(a)) == mv
+        for x in acts[:4]:
+            assert e.encode(e.decode(int(x))) == x
+        e.push(a)
+    t = e.terminal()
+    assert t[0] and [t[1], t[2]] == g["final"]
+
+
+def test_batched_positions_golden(kb):
+    from kami_b200 import api
+
+    z = np.load(os.path.join(G, "positions.npz"))
+    pos = api.as_positions(z["pos"])
+    planes = api.encode_planes(pos)
+    assert np.array_equal(planes, z["planes"].astype(np.float32).reshape(len(pos), -1))
+    acts, cnt = api.legal_actions(pos)
+    ev = api.static_eval(pos)
+    assert np.array_equal(ev, z["eval"])
+    for i in range(len(pos)):
+        t = z["terminal"][i]
+        if t[0] and t[1] <= 3:
+            continue  # draw by rule: the reference never generates moves there
+        assert cnt[i] == z["counts"][i], i
+        assert np.array_equal(acts[i][:cnt[i]], z["actions"][i][:cnt[i]]), i
+
+
+def test_batched_positions_vs_oracle_large(kb):
+    from kami_b200 import api
+
+    envs = H.sample_positions(1500, seed=21, max_ply=160)
+    pos = api.as_positions(np.stack([e.export() for e in envs]))
+    planes = api.encode_planes(pos)
+    acts, cnt = api.legal_actions(pos)
+    ev = api.static_eval(pos)
+    picks = np.zeros(len(envs), np.int32)
+    for i, e in enumerate(envs):
+        assert np.array_equal(planes[i], e.observe())
+        oa = e.actions()
+        assert cnt[i] == len(oa) and np.array_equal(acts[i][:cnt[i]], oa), i
+        assert ev[i] == e.eval()
+        picks[i] = oa[i % len(oa)]
+    nxt = api.apply_actions(pos, picks)
+    for i, e in enumerate(envs):
+        e.push(int(picks[i]))
+        assert np.array_equal(nxt[i:i + 1].view(np.uint8).reshape(-1), e.export()), i
+
+
+def test_empty_batches(kb):
+    from kami_b200 import api
+
+    pos = np.zeros(0, api.POSITION_DTYPE)
+    assert api.encode_planes(pos).shape == (0, 1920)
+    assert api.legal_actions(pos)[1].shape == (0,)
+
+
+# ---- MCTS ----------------------------------------------------------------------------------------
+def _cfg(kb, **kw):
+    from kami_b200 import api
+
+    return api.tree_cfg(**kw)
+
+
+@pytest.mark.parametrize("name", list(MCTS_CASES))
+def test_mcts_known_answers_golden(kb, name):
+    """Visit counts and whole-tree digests identical to the reference when both sides are fed the
+    same network outputs (noise off)."""
+    cfg, budget, moves, seed, vmode = MCTS_CASES[name]
+    known = json.load(open(os.path.join(G, "mcts_known.json")))[name]
+    t = kb.MCTS(cfg=_cfg(kb, **cfg))
+    nxt = mcts_stream(seed)
+    for rec in known:
+        while t.n() < budget:
+            ok, _ = t.select()
+            if not ok:
+                continue
+            p, v = nxt(vmode)
+            t.expand(p, v)
+        a, n, w, p = t.root_children()
+        assert a.tolist() == rec["actions"] and n.tolist() == rec["visits"]
+        d, c = t.digest()
+        assert (str(d), c) == (rec["digest"], rec["nodes"])
+        assert float(t.root_w()) == rec["root_w"]
+        pick = t.pick(0.0)
+        assert pick == rec["pick"]
+        t.push(pick)
+
+
+def test_mcts_vs_oracle_with_compaction(kb):
+    """Small node capacity so the copying collector runs at (almost) every push."""
+    cfg = dict(noise_weight=0.0, **H.DEF_YML)
+    t = kb.MCTS(cfg=_cfg(kb, **cfg), node_capacity=4096)
+    o = H.OracleMcts(H.default_cfg(**cfg))
+    rng = np.random.RandomState(9)
+    for mv in range(14):
+        while o.n() < 48:
+            so, oo = o.select()
+            sd, od = t.select()
+            assert so == sd
+            if not so:
+                continue
+            assert np.array_equal(oo, od)
+            p = rng.rand(H.PSIZE).astype(np.float32)
+            p /= p.sum()
+            v = float(np.float32(rng.rand() * 2 - 1))
+            o.expand(p, v)
+            t.expand(p, v)
+        assert t.n() == o.n() and t.digest() == o.digest()
+        assert np.array_equal(t.snapshot(), o.snapshot())
+        # temperature pick with an injected uniform: same cumulative walk on both sides
+        u = float(rng.rand())
+        a = o.pick(1.0, u)
+        assert t.pick(1.0, u) == a
+        o.push(a)
+        t.push(a)
+        assert np.array_equal(t.root_position().view(np.uint8).reshape(-1), o.env.export())
+        if o.env.terminal()[0]:
+            break
+
+
+def test_mcts_errors(kb):
+    from kami_b200 import KamiError
+
+    t = kb.MCTS(cfg=_cfg(kb, noise_weight=0.0))
+    with pytest.raises(KamiError):  # "no children to pick from" (mcts.h:139)
+        t.pick(0.0)
+    with pytest.raises(KamiError):  # expand without a selected leaf
+        t.expand(np.zeros(H.PSIZE, np.float32), 0.0)
+    ok, _ = t.select()
+    assert ok
+    t.expand(np.full(H.PSIZE, 1.0 / H.PSIZE, np.float32), 0.0)
+    with pytest.raises(KamiError):  # "no child for action" (mcts.h:129)
+        t.push(4671)
+
+
+def test_pool_batched_select_expand_vs_oracle(kb):
+    """kb_pool_select / kb_pool_expand on 96 trees == 96 independent oracle trees."""
+    cfg = dict(noise_weight=0.0, **H.DEF_YML)
+    n = 96
+    pool = kb.TreePool(n, 1 << 15, _cfg(kb, **cfg))
+    orc = [H.OracleMcts(H.default_cfg(**cfg)) for _ in range(n)]
+    rng = np.random.RandomState(4)
+    for it in range(40):
+        pool.select()
+        leaves = pool.leaf_positions()
+        pol = rng.rand(n, H.PSIZE).astype(np.float32)
+        pol /= pol.sum(1, keepdims=True)
+        val = (rng.rand(n) * 2 - 1).astype(np.float32)
+        for i, o in enumerate(orc):
+            while not o.select()[0]:
+                pass
+            assert np.array_equal(leaves[i:i + 1].view(np.uint8).reshape(-1), o.env.export()), (it, i)
+            o.expand(pol[i], float(val[i]))
+        pool.expand(pol, val)
+    for i in (0, 17, n - 1):
+        assert pool.tree(i).digest() == orc[i].digest()
+
+
+# ---- network ---------------------------------------------------------------------------------------
+def _kl(p, q):
+    return float((p * (np.log(p + 1e-30) - np.log(q + 1e-30))).sum(1).max())
+
+
+def _check_net(kb, F, R, B, seed, tol_v=1e-2, tol_kl=1e-3):
+    params = NO.init_params(F, R, seed=seed)
+    net = kb.NN(F, R)
+    net.load_blob(NO.pack_blob(params, F, R))
+    envs = H.sample_positions(B, seed=seed + 1)
+    obs = np.stack([e.observe() for e in envs])
+    pol, val = net.forward_full(obs)
+    op, ov = NO.forward(params, obs)
+    dv, kl = float(np.abs(val - ov).max()), _kl(op, pol)
+    print("net F=%d R=%d B=%d: max|dvalue|=%.3e  KL(ref||new)=%.3e  max|dpolicy|=%.3e" % (F, R, B, dv, kl, np.abs(pol - op).max()))
+    assert np.abs(pol.sum(1) - 1).max() < 1e-4
+    assert dv <= tol_v and kl <= tol_kl  # BASELINE.json north_star tolerances
+    # legal-renormalised distribution (what MCTS::expand consumes)
+    for i, e in enumerate(envs[:16]):
+        a = e.actions()
+        pr, pn = op[i][a] / op[i][a].sum(), pol[i][a] / pol[i][a].sum()
+        assert float((pr * (np.log(pr + 1e-30) - np.log(pn + 1e-30))).sum()) <= tol_kl
+    return net, params, obs, (pol, val), (op, ov)
+
+
+def test_conv1_layer_exact_structure(kb):
+    """R = 0: the tower output is conv1+BN+ReLU alone -- isolates the tcgen05 tile mapping."""
+    F = 64
+    params = NO.init_params(F, 0, seed=5)
+    net = kb.NN(F, 0)
+    net.load_blob(NO.pack_blob(params, F, 0))
+    envs = H.sample_positions(9, seed=8)
+    obs = np.stack([e.observe() for e in envs])
+    net.forward_full(obs)
+    x = np.ascontiguousarray(obs.reshape(-1, 8, 8, 30).transpose(0, 3, 1, 2))
+    ref = np.maximum(NO._bn(NO._conv(x, params["conv1.weight"], params["conv1.bias"]), params, "batchnorm1"), 0)
+    for b in (0, 6, 7, 8):  # boards in the first and second item
+        inp = net.debug_activation(0, b)
+        assert np.array_equal(inp[:30].reshape(30, 8, 8), x[b])
+        got = net.debug_activation(1, b).reshape(F, 8, 8)
+        err = np.abs(got - ref[b]).max()
+        assert err < 0.05, (b, err)
+
+
+def test_net_golden_reference_outputs(kb):
+    """Against outputs of the reference's own LibTorch fp32 network (tests/golden)."""
+    z = np.load(os.path.join(G, "nn_f64r2.npz"))
+    params = NO.init_params(64, 2, seed=int(z["param_seed"]))
+    net = kb.NN(64, 2)
+    net.load_blob(NO.pack_blob(params, 64, 2))
+    obs = z["obs"].astype(np.float32)
+    pol, val = net.forward_full(obs)
+    assert np.abs(val - z["value256"]).max() <= 1e-2
+    assert _kl(z["policy"], pol) <= 1e-3
+    ip, iv = net.infer(obs)
+    assert np.abs(iv - z["infer_value"]).max() <= 1e-2
+    assert np.array_equal(iv, val[0, :len(iv)])  # (Q1) value[i] = vh.flat[i]
+
+
+@pytest.mark.parametrize("F,R,B", [(64, 2, 256), (256, 2, 64), (128, 1, 20)])
+def test_net_vs_oracle(kb, F, R, B):
+    _check_net(kb, F, R, B, seed=12)
+
+
+def test_net_batch_edges(kb):
+    """Ragged batches: 1 board, a full item (7), one past it (8)."""
+    params = NO.init_params(64, 1, seed=3)
+    net = kb.NN(64, 1)
+    net.load_blob(NO.pack_blob(params, 64, 1))
+    envs = H.sample_positions(8, seed=6)
+    obs = np.stack([e.observe() for e in envs])
+    full = net.forward_full(obs)
+    for b in (1, 7, 8):
+        pol, val = net.forward_full(obs[:b])
+        assert np.array_equal(pol, full[0][:b]) and np.array_equal(val, full[1][:b])
+
+
+def test_net_nan_guard(kb):
+    from kami_b200 import KamiError
+
+    params = NO.init_params(64, 0, seed=3)
+    params["valuefc.bias"][:] = np.nan
+    net = kb.NN(64, 0)
+    net.load_blob(NO.pack_blob(params, 64, 0))
+    with pytest.raises(KamiError):  # nn.cpp:176-180
+        net.infer(np.zeros((2, 1920), np.float32))
+
+
+# ---- the whole loop ---------------------------------------------------------------------------------
+def test_pool_step_selfplay_smoke(kb):
+    """Device-resident loop of selfplay.cpp:113-200; checks invariants the domain offers."""
+    F, R, n = 64, 2, 128
+    params = NO.init_params(F, R, seed=2)
+    net = kb.NN(F, R)
+    net.load_blob(NO.pack_blob(params, F, R))
+    cfg = _cfg(kb, noise_weight=0.05, selfplay_nodes=24, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5,
+               alpha_cutoff=20, seed=7, **H.DEF_YML)
+    pool = kb.TreePool(n, 1 << 14, cfg)
+    iters = 400
+    pool.step(net, iters)
+    s = pool.stats()
+    assert s["evals"] == n * iters  # exactly one leaf per tree per batch, batch always full
+    assert s["moves"] > n * 5 and s["children_created"] > s["evals"] * 5
+    assert s["path_nodes"] >= s["evals"]
+    obs, pi, z = pool.drain_samples(64)
+    if len(z):
+        assert np.allclose(pi.sum(1), 1.0, atol=1e-3) and set(np.unique(z)).issubset({-1.0, 0.0, 1.0})
+    # every tree still satisfies n(root) == 1 + sum(child visits) (+ terminal visits at the root = 0)
+    for i in (0, n // 2, n - 1):
+        t = pool.tree(i)
+        a, cn, w, p = t.root_children()
+        if len(cn):
+            assert t.n() == 1 + int(cn.sum())
+            assert abs(float(p.sum()) - 1.0) < 1e-3
+
+
+def test_pool_step_matches_hostio_path(kb):
+    """kb_pool_step (resident) and kb_pool_step_hostio (reference-shaped host round trip) drive
+    identical searches when noise is off."""
+    F, R, n = 64, 1, 32
+    params = NO.init_params(F, R, seed=4)
+    net = kb.NN(F, R)
+    net.load_blob(NO.pack_blob(params, F, R))
+    kw = dict(noise_weight=0.0, selfplay_nodes=16, seed=1, **H.DEF_YML)
+    a, b = kb.TreePool(n, 1 << 14, _cfg(kb, **kw)), kb.TreePool(n, 1 << 14, _cfg(kb, **kw))
+    a.step(net, 60)
+    obs = np.zeros((n, 1920), np.float32)
+    pol = np.zeros((n, H.PSIZE), np.float32)
+    val = np.zeros(n, np.float32)
+    b.step_hostio(net, 60, obs, pol, val)
+    for i in (0, 5, n - 1):
+        assert a.tree(i).digest() == b.tree(i).digest()
+    assert a.stats()["moves"] == b.stats()["moves"]
