@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- self-play hot path throughput on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]/[3]): 1024 concurrent self-play games per GPU with
+device-resident PUCT trees, options.def.yml settings (2x64 residual tower, 1024-node budget per
+move, cpuct 1.5, bootstrap 20 %), random-init weights, synthetic positions (the games themselves).
+A "step" is one pass of the hot path over one batch: every tree selects a leaf (terminals
+absorbed, moves made at the node budget), leaves are encoded, the tower + heads run, results are
+expanded and backed up  ==  1024 NN evaluations per GPU.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job NN evals/s with everything resident in HBM;
+`e2e` = the same loop through the reference-shaped host-buffer API (kb_pool_step_hostio:
+observations and policy/value rows cross PCIe every step, like kami::NN::infer / MCTS::expand).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+TREES_PER_GPU = 1024
+FILTERS, RESIDUALS = 64, 2          # options.def.yml:29,53
+SELFPLAY_NODES = 1024               # options.def.yml selfplay_nodes
+NODE_CAPACITY = 1 << 17
+PREROLL_STEPS = 1536                # untimed: grows the synthetic trees to steady state (first moves made)
+METRIC = "selfplay_nn_evals_per_sec"
+UNIT = "evals/s"
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+
+def reduce_max(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref, compiled from
+# /root/reference) on the host cores -- selfplay.cpp:113-200 with the reference's objects
+# ---------------------------------------------------------------------------------------------
+def reference_loop(seconds_budget, threads, ibatch, steps=None, iters_per_step=4):
+    """Runs `threads` inference threads x `ibatch` reference MCTS trees sharing one reference NN
+    (LibTorch CPU, force_cpu), exactly the structure of Selfplay::inference_main.  Returns
+    (evals, moves, seconds, kind)."""
+    import harness as H
+
+    if H.ref_core() is None or H.ref_nn_lib() is None:
+        return _port_loop(seconds_budget, ibatch, steps, iters_per_step)
+    cfg = H.default_cfg(noise_weight=0.05, **H.DEF_YML)
+    nn = H.RefNN(FILTERS, RESIDUALS, seed=1, force_cpu=True)
+    H.ref_nn_lib().ref_nn_set_threads(max(1, os.cpu_count() or 1))
+    counts = [[0, 0] for _ in range(threads)]
+    stop = threading.Event()
+    limit = None if steps is None else steps * iters_per_step
+
+    def worker(tid):
+        trees = [H.RefMcts(cfg) for _ in range(ibatch)]
+        batch = np.zeros((ibatch, H.OBSIZE), np.float32)
+        it = 0
+        while not stop.is_set() and (limit is None or it < limit):
+            for i, t in enumerate(trees):
+                while True:
+                    ok = False
+                    while t.n() < SELFPLAY_NODES:
+                        ok, obs = t.select()
+                        if ok:
+                            break
+                    if ok:
+                        batch[i] = obs
+                        break
+                    ply = t.env.ply()  # selfplay.cpp:153-156 with options.def.yml's schedule
+                    a = t.pick(0.95 ** ply if ply < 20 else 0.5)
+                    t.push(a)
+                    counts[tid][1] += 1
+                    if t.env.terminal()[0]:
+                        t.reset()
+            pol, val = nn.infer(batch)
+            for i, t in enumerate(trees):
+                t.expand(pol[i], float(val[i]))
+            counts[tid][0] += ibatch
+            it += 1
+
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
+    t0 = time.time()
+    for t in ths:
+        t.start()
+    if limit is None:
+        time.sleep(seconds_budget)
+        stop.set()
+    for t in ths:
+        t.join()
+    dt = time.time() - t0
+    return sum(c[0] for c in counts), sum(c[1] for c in counts), dt, "reference"
+
+
+def _port_loop(seconds_budget, ibatch, steps, iters_per_step):
+    """Fallback when oracle/_ref is absent: the oracle port (C restatement + numpy network)."""
+    import harness as H
+    import nn_oracle as NO
+
+    params = NO.init_params(FILTERS, RESIDUALS, seed=1)
+    cfg = H.default_cfg(noise_weight=0.0, **H.DEF_YML)
+    trees = [H.OracleMcts(cfg) for _ in range(ibatch)]
+    evals = moves = it = 0
+    limit = None if steps is None else steps * iters_per_step
+    t0 = time.time()
+    while (limit is None and time.time() - t0 < seconds_budget) or (limit is not None and it < limit):
+        batch = np.zeros((ibatch, H.OBSIZE), np.float32)
+        for i, t in enumerate(trees):
+            while True:
+                ok = False
+                while t.n() < SELFPLAY_NODES:
+                    ok, obs = t.select()
+                    if ok:
+                        break
+                if ok:
+                    batch[i] = obs
+                    break
+                t.push(t.pick(0.0))
+                moves += 1
+                if t.env.terminal()[0]:
+                    t.reset()
+        pol, val = NO.infer(params, batch)
+        for i, t in enumerate(trees):
+            t.expand(pol[i], float(val[i]))
+        evals += ibatch
+        it += 1
+    return evals, moves, time.time() - t0, "port"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = 3   # options.def.yml inference_threads
+    ibatch = 16   # options.def.yml selfplay_batch
+    iters_per_step = 4
+    # warmup
+    reference_loop(0, threads, ibatch, steps=max(1, args.warmup), iters_per_step=1)
+    evals, moves, dt, kind = reference_loop(0, threads, ibatch, steps=args.steps, iters_per_step=iters_per_step)
+    v = evals / dt
+    cores = os.cpu_count() or 1
+    sample = "%d steps x %d iterations of %d threads x %d trees (selfplay.cpp:113-200), LibTorch CPU fp32, %d torch threads" % (
+        args.steps, iters_per_step, threads, ibatch, cores)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "positions_per_sec": moves / dt},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config():
+    return {"workload": "1024 concurrent self-play games per GPU, device-resident PUCT trees, options.def.yml "
+                        "(2x64 tower, 1024-node budget/move, cpuct 1.5, bootstrap 20%, noise 0.05), random-init weights",
+            "trees_per_gpu": TREES_PER_GPU, "filters": FILTERS, "residuals": RESIDUALS, "selfplay_nodes": SELFPLAY_NODES,
+            "evals_per_step_per_gpu": TREES_PER_GPU,
+            "l2": "inputs larger than L2: live node pools ~0.6 MB x 1024 trees per GPU >> 126 MB, no flush"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local, dist):
+    import harness as H
+    import kami_b200
+    import nn_oracle as NO
+    from kami_b200 import api
+
+    api.init(local)
+    L = kami_b200.lib()
+    hbm_peak, tf_peak, tf_sustained, peak_kind = peaks()
+
+    net = kami_b200.NN(FILTERS, RESIDUALS)
+    net.load_blob(NO.pack_blob(NO.init_params(FILTERS, RESIDUALS, seed=1), FILTERS, RESIDUALS))
+    kw = dict(noise_weight=0.05, selfplay_nodes=SELFPLAY_NODES, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5,
+              alpha_cutoff=20, draw_value_pct=50, **H.DEF_YML)
+    pool = kami_b200.TreePool(TREES_PER_GPU, NODE_CAPACITY, api.tree_cfg(seed=1000 + rank, **kw))
+
+    def timed_steps(fn, k):
+        ms = C.c_float()
+        barrier(dist, local)
+        L.kb_dev_sync()
+        L.kb_timer_start()
+        fn(k)
+        L.kb_timer_stop(C.byref(ms))
+        barrier(dist, local)
+        return reduce_max(dist, local, ms.value)
+
+    # state preparation (untimed): grow the synthetic games to steady state, then W warm-up steps
+    if args.preroll > 0:
+        pool.step(net, args.preroll)
+    pool.step(net, max(3, args.warmup))
+    pool.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_steps(lambda k: pool.step(net, k), args.steps)
+    clocks = sampler.stop()
+    st = pool.stats()
+    ph = pool.phase_ms()
+    evals_local = float(st["evals"])
+    evals = reduce_sum(dist, local, evals_local)
+    moves = reduce_sum(dist, local, float(st["moves"]))
+    value = evals / (ms * 1e-3)
+
+    # roofline of the dominant kernel of the step (timed live with CUDA events inside kb_pool_step)
+    t_f, h_f = net.flops()
+    phases = {"select+encode": ph["select"], "tower+heads": ph["tower"], "expand+backup": ph["expand"]}
+    dominant = max(phases, key=phases.get)
+    if dominant == "tower+heads":
+        achieved = (t_f + h_f) * TREES_PER_GPU / (ph["tower"] * 1e-3) / 1e12
+        roof = {"kernel": "k_conv x%d + heads (tcgen05 tower, %dx%d)" % (1 + 2 * RESIDUALS + 2, RESIDUALS, FILTERS),
+                "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "traffic": None, "peak_kind": peak_kind + " burst",
+                "algorithmic": "%.3f MFLOP/position x %d positions per launch group" % ((t_f + h_f) / 1e6, TREES_PER_GPU)}
+    else:
+        per_step = (12.0 * st["children_scanned"] + 16.0 * st["path_nodes"] + 16.0 * st["children_created"]) / max(1, args.steps)
+        per_step += 3904.0 * TREES_PER_GPU
+        dur = (ph["select"] + ph["expand"]) * 1e-3
+        achieved = per_step / dur / 1e9
+        roof = {"kernel": "k_pool_select + k_pool_expand", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                "algorithmic": "12 B x children scanned + 16 B x path nodes + 16 B x children created + 3904 B planes per leaf"}
+
+    # end to end through the reference-shaped host-buffer API (pinned host memory)
+    n = TREES_PER_GPU
+    bufs = []
+
+    def pinned(shape):
+        nbytes = int(np.prod(shape)) * 4
+        p = C.c_void_p()
+        api._ck(L.kb_host_alloc_pinned(C.byref(p), nbytes))
+        bufs.append(p)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(int(np.prod(shape)),)).reshape(shape)
+
+    obs_h, pol_h, val_h = pinned((n, 1920)), pinned((n, 4672)), pinned((n,))
+    e2e_steps = max(3, min(args.steps, 400))
+    pool.step_hostio(net, 3, obs_h, pol_h, val_h)
+    pool.reset_stats()
+    ms_e2e = timed_steps(lambda k: pool.step_hostio(net, k, obs_h, pol_h, val_h), e2e_steps)
+    evals_e2e = reduce_sum(dist, local, float(pool.stats()["evals"]))
+    e2e_value = evals_e2e / (ms_e2e * 1e-3)
+    h2d = n * 1920 * 4 + n * 4672 * 4 + n * 4   # observations into NN::infer, policy + value into MCTS::expand
+    d2h = n * 1920 * 4 + n * 4672 * 4 + n * 4   # leaf observations out, policy + value out
+
+    extras = {}
+    cpu = None
+    if rank == 0 and not args.no_extras:
+        # 20x256 tower (BASELINE config 5's network) forward only: % of dense BF16 peak at batch 1024
+        try:
+            big = kami_b200.NN(256, 20)
+            big.load_blob(NO.pack_blob(NO.init_params(256, 20, seed=1), 256, 20))
+            B = 1024
+            planes, pol, val = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            api._ck(L.kb_dev_alloc(C.byref(planes), L.kb_net_planes_bytes(B)))
+            api._ck(L.kb_dev_alloc(C.byref(pol), B * 4672 * 4))
+            api._ck(L.kb_dev_alloc(C.byref(val), B * 256 * 4))
+            for _ in range(3):
+                api._ck(L.kb_net_forward_dev(big.h, planes, B, pol, val))
+            msb = C.c_float()
+            L.kb_dev_sync()
+            L.kb_timer_start()
+            reps = 5
+            for _ in range(reps):
+                api._ck(L.kb_net_forward_dev(big.h, planes, B, pol, val))
+            L.kb_timer_stop(C.byref(msb))
+            tb, hb = big.flops()
+            tfl = tb * B * reps / (msb.value * 1e-3) / 1e12
+            extras["tower_20x256"] = {"batch": B, "ms_per_forward": msb.value / reps, "tower_tflops": tfl,
+                                      "frac_of_bf16_peak": tfl / tf_peak, "frac_of_sustained": tfl / tf_sustained,
+                                      "evals_per_sec": B * reps / (msb.value * 1e-3), "peak_kind": peak_kind}
+            for p in (planes, pol, val):
+                L.kb_dev_free(p)
+            del big
+        except Exception as e:  # never lose the bench line to the extra measurement
+            extras["tower_20x256"] = {"error": str(e)}
+        if world == 1:
+            ev, mv, dt, kind = reference_loop(12.0, 3, 16)
+            cores = os.cpu_count() or 1
+            cpu = {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": kind, "positions_per_sec": mv / dt,
+                   "sample": "%.0f s of 3 inference threads x 16 trees (options.def.yml) on %d host cores, %s" % (
+                       dt, cores, "unmodified reference Env/MCTS + LibTorch CPU fp32 NN" if kind == "reference" else "oracle port")}
+
+    for p in bufs:
+        L.kb_host_free_pinned(p)
+    if rank != 0:
+        return
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(),
+        "positions_per_sec": moves / (ms * 1e-3),
+        "phase_ms_last_step": phases,
+        "roofline": roof,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks,
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    out.update(extras)
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preroll", type=int, default=PREROLL_STEPS, help="untimed state-preparation steps (profiling runs shorten it)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 20x256 tower and CPU baseline legs (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if args.steps == 2000 and args.warmup == 200:  # defaults sized for the GPU arm; keep the CPU arm to ~1 min
+            args.steps, args.warmup = 40, 3
+        run_reference(args, rank)
+        return
+    rank, world, local, dist = dist_setup(args.gpus)
+    try:
+        run_ours(args, rank, world, local, dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

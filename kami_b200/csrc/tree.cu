@@ -343,11 +343,12 @@ __device__ void compact_into_other_space(const PoolDev& P, int t, u32 keep) {
         dm[0] = sm[keep];
     }
     __syncwarp();
-    u32 tail = 1;
-    for (u32 head = 0; head < tail; head += 32) {
+    u32 tail = 1, head = 0;
+    while (head < tail) {  // [head, tail) = copied nodes whose children still live in the old space
+        const u32 wave = tail - head < 32u ? tail - head : 32u;
         const u32 i = head + lane;
         u32 k = 0, oc = 0;
-        if (i < tail) {
+        if ((u32)lane < wave) {
             k = dm[i] >> 16;
             oc = dn[i].child0;
         }
@@ -373,6 +374,7 @@ __device__ void compact_into_other_space(const PoolDev& P, int t, u32 keep) {
             }
         }
         tail += total;
+        head += wave;
         __syncwarp();
     }
     if (lane == 0) {
@@ -1099,6 +1101,7 @@ struct kb_pool {
     Pos* leaf_dev;
     float* policy_dev;   // [n][4672]
     float* value_dev;    // [n][256]
+    float* obs_batch_dev; // [n][1920] staging of the host-I/O path
     unsigned long long launches;
     cudaEvent_t ev[6];
     kb_phase_ms last;
@@ -1216,6 +1219,7 @@ int kb_pool_destroy(kb_pool* p) {
     cudaFree(d.traj); cudaFree(d.replay); cudaFree(d.replay_head);
     cudaFree(p->obs_dev); cudaFree(p->pol_dev); cudaFree(p->int_dev); cudaFree(p->u64_dev); cudaFree(p->info_dev);
     cudaFree(p->child_i); cudaFree(p->child_f); cudaFree(p->leaf_dev); cudaFree(p->policy_dev); cudaFree(p->value_dev);
+    cudaFree(p->obs_batch_dev);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(p->ev[i]);
     delete p;
     return KB_OK;
@@ -1421,27 +1425,38 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters) {
     return KB_OK;
 }
 
-// Reference-shaped data flow: every iteration's observations go to the host and come back
-// (kami::NN::infer takes and returns host buffers, nn.cpp:155-187).
+// Reference-shaped data flow: every iteration's observations go to the host and come back, and so
+// do the policy / value rows (kami::NN::infer takes and returns host buffers, nn.cpp:155-187;
+// MCTS::expand takes a host policy row, mcts.h:257).  Buffers should be pinned.
 int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, float* policy_host, float* value_host) {
     KB_ARG(p && net && iters > 0 && obs_host && policy_host && value_host, "pool/net/iters/buffers");
-    const int n = p->d.n_trees;
+    const size_t n = (size_t)p->d.n_trees;
     cudaStream_t st = main_stream();
+    if (!p->obs_batch_dev) KB_CUDA(cudaMalloc(&p->obs_batch_dev, sizeof(float) * KB_OBSIZE * n));
+    int r = net_reserve(net, (int)n);
+    if (r) return r;
     for (int it = 0; it < iters; ++it) {
-        int r = kb_pool_select(p);
-        if (r) return r;
-        float* obs_dev = nullptr;
-        DevBuf ob;
-        if ((r = ob.alloc(sizeof(float) * KB_OBSIZE * (size_t)n))) return r;
-        obs_dev = (float*)ob.p;
-        if ((r = kb_encode_planes_dev((const kb_position*)p->leaf_dev, n, obs_dev))) return r;
-        KB_CUDA(cudaMemcpyAsync(obs_host, obs_dev, sizeof(float) * KB_OBSIZE * (size_t)n, cudaMemcpyDeviceToHost, st));
+        // select + Env::observe on the device, observations out to the caller's buffer
+        k_pool_select<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, nullptr, p->leaf_dev);
+        KB_CUDA(cudaGetLastError());
+        if ((r = kb_encode_planes_dev((const kb_position*)p->leaf_dev, (int)n, p->obs_batch_dev))) return r;
+        KB_CUDA(cudaMemcpyAsync(obs_host, p->obs_batch_dev, sizeof(float) * KB_OBSIZE * n, cudaMemcpyDeviceToHost, st));
+        if ((r = pool_check(p, true))) return r;
+        // NN::infer(host obs) -> host policy / value
+        KB_CUDA(cudaMemcpyAsync(p->obs_batch_dev, obs_host, sizeof(float) * KB_OBSIZE * n, cudaMemcpyHostToDevice, st));
+        if ((r = obs_to_tall_launch(p->obs_batch_dev, (int)n, net_input_planes(net), st))) return r;
+        if ((r = net_forward_async(net, net_input_planes(net), (int)n, p->policy_dev, p->value_dev, st))) return r;
+        KB_CUDA(cudaMemcpyAsync(policy_host, p->policy_dev, sizeof(float) * KB_PSIZE * n, cudaMemcpyDeviceToHost, st));
+        KB_CUDA(cudaMemcpyAsync(value_host, p->value_dev, sizeof(float) * n, cudaMemcpyDeviceToHost, st));  // vh.flat[i] (Q1)
         KB_CUDA(cudaStreamSynchronize(st));
-        p->launches += 1;
-        if ((r = kb_net_infer(net, obs_host, n, policy_host, value_host))) return r;
-        if ((r = kb_pool_expand(p, policy_host, value_host, 0))) return r;
+        // MCTS::expand(host policy row, value)
+        KB_CUDA(cudaMemcpyAsync(p->policy_dev, policy_host, sizeof(float) * KB_PSIZE * n, cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaMemcpyAsync(p->value_dev, value_host, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+        k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 0, 0);
+        KB_CUDA(cudaGetLastError());
+        p->launches += 4 + (unsigned long long)net_launches_per_forward(net);
     }
-    return KB_OK;
+    return pool_check(p, true);
 }
 
 int kb_pool_get_stats(kb_pool* p, kb_pool_stats* out) {

@@ -145,7 +145,7 @@ def test_mcts_vs_oracle_with_compaction(kb):
             assert so == sd
             if not so:
                 continue
-            assert np.array_equal(oo, od)
+            assert np.array_equal(oo, od), (mv, o.n(), np.nonzero(oo != od)[0][:8], oo[oo != od][:8], od[oo != od][:8])
             p = rng.rand(H.PSIZE).astype(np.float32)
             p /= p.sum()
             v = float(np.float32(rng.rand() * 2 - 1))
