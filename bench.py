@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 TREES_PER_GPU = 1024
 FILTERS, RESIDUALS = 64, 2          # options.def.yml:29,53
 SELFPLAY_NODES = 1024               # options.def.yml selfplay_nodes
-NODE_CAPACITY = 1 << 17
+NODE_CAPACITY = 1 << 19  # 2 x 10 MB per tree: the copying collector runs about once per 40 moves
 PREROLL_STEPS = 1536                # untimed: grows the synthetic trees to steady state (first moves made)
 METRIC = "selfplay_nn_evals_per_sec"
 UNIT = "evals/s"

@@ -250,6 +250,315 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused forward for the 64-filter network (options.def.yml: filters 64): ONE kernel per batch.
+// A CTA owns an item (7 boards).  Activations never leave shared memory between layers:
+//
+//   region  = [ X : 8 planes | Y : 8 planes ]   (160 KB, tall-image planes, pads zero)
+//   P (input, 4 planes) lands in Y; conv1: P -> X; residual r: X -> Y -> X (+skip from X);
+//   value head (CUDA cores) reads X; policy conv 1x1: X -> H (16 planes, overlays X|Y);
+//   policy conv2 1x1: H -> fp32 logits (overlay), softmax over 4672 per board -> global.
+//
+// Warp roles: warp 0 bulk-TMA producer (input planes + all weight blocks in consumption
+// order through a 3-stage ring), warp 1 tcgen05.mma issuer, warp 2 TMEM allocator, warps 4-11
+// epilogue (two warps per TMEM lane quarter, splitting the accumulator columns).
+// ------------------------------------------------------------------------------------------
+struct FusedLayer {
+    int src_off, dst_off;  // byte offsets of the source / destination planes inside the region
+    int chunks_in;         // 8-channel planes read
+    int n;                 // output channels computed (UMMA N)
+    int ntaps, relu, skip, bias_off;
+    int kind;              // 0 bf16 activation to smem, 1 fp32 logits to smem
+    uint32_t idesc;
+};
+struct FusedParams {
+    const uint4* planes;
+    const uint4* w;
+    const float* bias;
+    float* policy;
+    float* value256;
+    const float* wv;
+    const float* fct;
+    const float* fcb;
+    int* nan_flag;
+    float bv;
+    int n_bias, items, boards, n_layers, tower_layers;
+    FusedLayer layer[16];
+};
+constexpr int FZ_HDR = 8192;                  // barriers, tmem slot, value scratch, biases
+constexpr int FZ_REGION = 16 * PLANE_BYTES;   // 163840
+constexpr int FZ_STAGE = 16384;
+constexpr int FZ_NSTAGE = 3;
+constexpr int FZ_SMEM = FZ_HDR + FZ_REGION + FZ_NSTAGE * FZ_STAGE;
+constexpr int FZ_EPI_THREADS = 256;
+static_assert(FZ_SMEM <= 232448, "fused tower shared memory budget");
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ FusedParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s0 = ptx::smem_u32(smem);
+    auto b_full = [&](int s) { return s0 + 8u * s; };
+    auto b_empty = [&](int s) { return s0 + 8u * (4 + s); };
+    const uint32_t p_full = s0 + 8u * 8, t_full = s0 + 8u * 9, act_ready = s0 + 8u * 10, region_clean = s0 + 8u * 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    float* vbuf = reinterpret_cast<float*>(smem + 512);     // [7][64] value-conv outputs
+    float* sbias = reinterpret_cast<float*>(smem + 2560);   // all folded biases
+    uint8_t* region = smem + FZ_HDR;
+    const uint32_t region_s = s0 + FZ_HDR;
+    const uint32_t ring_s = region_s + FZ_REGION;
+
+    const int my_items = P.items > (int)blockIdx.x ? (P.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FZ_NSTAGE; ++s) {
+            ptx::mbar_init(b_full(s), 1);
+            ptx::mbar_init(b_empty(s), 1);
+        }
+        ptx::mbar_init(p_full, 1);
+        ptx::mbar_init(t_full, 1);
+        ptx::mbar_init(act_ready, 8);
+        ptx::mbar_init(region_clean, 8);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+        ptx::tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < P.n_bias; i += blockDim.x) sbias[i] = P.bias[i];
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== producer =====
+        int stage = 0, sphase = 0;
+        for (int ii = 0; ii < my_items; ++ii) {
+            const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+            ptx::mbar_wait(region_clean, ii & 1);
+            ptx::mbar_arrive_expect_tx(p_full, IN_CHUNKS * PLANE_BYTES);
+            ptx::bulk_g2s(region_s + 8 * PLANE_BYTES, P.planes + (size_t)item * IN_CHUNKS * PLANE_PIX, IN_CHUNKS * PLANE_BYTES, p_full);
+            const uint4* w = P.w;
+            for (int l = 0; l < P.n_layers; ++l) {
+                const FusedLayer& L = P.layer[l];
+                const int slice = L.chunks_in < 8 ? L.chunks_in : 8;
+                const int nblocks = L.ntaps * (L.chunks_in / slice);
+                const uint32_t bytes = (uint32_t)(slice * L.n * 16);
+                for (int b = 0; b < nblocks; ++b) {
+                    ptx::mbar_wait(b_empty(stage), sphase ^ 1);
+                    ptx::mbar_arrive_expect_tx(b_full(stage), bytes);
+                    ptx::bulk_g2s(ring_s + stage * FZ_STAGE, w, bytes, b_full(stage));
+                    w += bytes / 16;
+                    if (++stage == FZ_NSTAGE) {
+                        stage = 0;
+                        sphase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        int stage = 0, sphase = 0;
+        uint32_t act_phase = 0;
+        for (int ii = 0; ii < my_items; ++ii) {
+            for (int l = 0; l < P.n_layers; ++l) {
+                const FusedLayer& L = P.layer[l];
+                if (l == 0) ptx::mbar_wait(p_full, ii & 1);
+                else {
+                    ptx::mbar_wait(act_ready, act_phase);  // previous layer written to smem, TMEM drained
+                    act_phase ^= 1;
+                }
+                ptx::tc_fence_after();
+                const int slice = L.chunks_in < 8 ? L.chunks_in : 8;
+                const int kslices = L.chunks_in / slice;
+                const uint32_t a_src = region_s + L.src_off;
+                for (int ks = 0; ks < kslices; ++ks)
+                    for (int tap = 0; tap < L.ntaps; ++tap) {
+                        const int dy = L.ntaps == 9 ? tap / 3 - 1 : 0, dx = L.ntaps == 9 ? tap % 3 - 1 : 0;
+                        ptx::mbar_wait(b_full(stage), sphase);
+                        ptx::tc_fence_after();
+                        const uint32_t b_base = ring_s + stage * FZ_STAGE;
+                        for (int kk = 0; kk < slice / 2; ++kk) {
+                            const uint64_t bdesc = ptx::smem_desc(b_base + kk * 2 * (L.n * 16), L.n * 16, 128);
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) {
+                                const int px = (16 * mt + dy) * TALL_PITCH + 1 + dx;
+                                const uint32_t a_addr = (uint32_t)((int)(a_src + (ks * 8 + kk * 2) * PLANE_BYTES) + px * 16);
+                                const uint64_t adesc = ptx::smem_desc(a_addr, PLANE_BYTES, TALL_PITCH * 16);
+                                ptx::mma_bf16(tmem_base + mt * L.n, adesc, bdesc, L.idesc, (ks | tap | kk) != 0);
+                            }
+                        }
+                        ptx::mma_commit(b_empty(stage));
+                        if (++stage == FZ_NSTAGE) {
+                            stage = 0;
+                            sphase ^= 1;
+                        }
+                    }
+                ptx::mma_commit(t_full);
+            }
+            // the last layer's epilogue also signals act_ready (TMEM drained) -- consume it
+            ptx::mbar_wait(act_ready, act_phase);
+            act_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps =====
+        const int e = warp - 4, q = e & 3, half = e >> 2;
+        const int et = threadIdx.x - 128;  // 0..255
+        uint32_t t_phase = 0;
+        for (int ii = 0; ii < my_items; ++ii) {
+            const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+            {   // pads must read as zero: clear the whole region, then hand it to the async proxy
+                uint4* r4 = reinterpret_cast<uint4*>(region);
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                for (int i = et; i < FZ_REGION / 16; i += FZ_EPI_THREADS) r4[i] = z;
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(region_clean);
+            }
+            for (int l = 0; l < P.n_layers; ++l) {
+                const FusedLayer& L = P.layer[l];
+                ptx::mbar_wait(t_full, t_phase);
+                t_phase ^= 1;
+                ptx::tc_fence_after();
+                if (l == P.tower_layers) epi_bar();  // every warp finished reading X for the value head
+                const int ncg = L.n / 16;
+                const int cg0 = half == 0 ? 0 : (ncg + 1) / 2, cg1 = half == 0 ? (ncg + 1) / 2 : ncg;
+#pragma unroll 1
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int r = 32 * q + lane;
+                    const int R = 16 * mt + (r >> 3), x = r & 7;
+                    const int slot = (R - 1) / 9, y = (R - 1) - slot * 9;
+                    const bool valid = R >= 1 && y < 8 && slot < NB;
+                    const int px = R * TALL_PITCH + 1 + x;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + mt * L.n;
+#pragma unroll 1
+                    for (int cg = cg0; cg < cg1; ++cg) {
+                        uint32_t v[16];
+                        ptx::tmem_ld16(taddr + cg * 16, v);
+                        ptx::tmem_ld_wait();
+                        if (!valid) continue;
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            f[j] = __uint_as_float(v[j]) + sbias[L.bias_off + cg * 16 + j];
+                            if (L.relu) f[j] = fmaxf(f[j], 0.0f);
+                        }
+                        if (L.kind == 1) {
+                            float* lg = reinterpret_cast<float*>(region) + (size_t)slot * KB_PSIZE + (y * 8 + x) * 73;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (cg * 16 + j < 73) lg[cg * 16 + j] = f[j];
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint4* dst = reinterpret_cast<uint4*>(region + L.dst_off) + (size_t)(cg * 2 + h) * PLANE_PIX + px;
+                                if (L.skip) {  // x = skip + relu(...), the skip is the destination itself (nn.cpp:31)
+                                    const uint4 s4 = *dst;
+                                    const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&s4);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 sv = __bfloat1622float2(sb[k]);
+                                        f[h * 8 + 2 * k] += sv.x;
+                                        f[h * 8 + 2 * k + 1] += sv.y;
+                                    }
+                                }
+                                uint32_t w4[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 b = __floats2bfloat162_rn(f[h * 8 + 2 * k], f[h * 8 + 2 * k + 1]);
+                                    w4[k] = *reinterpret_cast<const uint32_t*>(&b);
+                                }
+                                *dst = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                            }
+                        }
+                    }
+                }
+                fence_async_smem();       // generic-proxy smem writes -> visible to tcgen05.mma
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(act_ready);
+                if (l == P.tower_layers - 1) {
+                    // ---- value head on X (nn.cpp:83-88), overlapping the policy conv's MMAs ----
+                    epi_bar();  // X complete
+                    const uint4* X = reinterpret_cast<const uint4*>(region + P.layer[l].dst_off);
+                    for (int i = et; i < NB * 64; i += FZ_EPI_THREADS) {
+                        const int slot = i >> 6, pix = i & 63;
+                        const int px = tall_pixel(slot, pix);
+                        float acc = P.bv;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint4 a4 = X[c * PLANE_PIX + px];
+                            const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&a4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 av = __bfloat1622float2(ab[k]);
+                                acc = fmaf(av.x, __ldg(P.wv + c * 8 + 2 * k), acc);
+                                acc = fmaf(av.y, __ldg(P.wv + c * 8 + 2 * k + 1), acc);
+                            }
+                        }
+                        vbuf[i] = fmaxf(acc, 0.0f);
+                    }
+                    epi_bar();
+                    float o[NB];
+                    const float b0 = __ldg(P.fcb + et);
+#pragma unroll
+                    for (int s = 0; s < NB; ++s) o[s] = b0;
+#pragma unroll 4
+                    for (int p = 0; p < 64; ++p) {
+                        const float wgt = __ldg(P.fct + p * 256 + et);
+#pragma unroll
+                        for (int s = 0; s < NB; ++s) o[s] = fmaf(vbuf[s * 64 + p], wgt, o[s]);
+                    }
+#pragma unroll
+                    for (int s = 0; s < NB; ++s) {
+                        const int board = item * NB + s;
+                        if (board < P.boards) {
+                            const float t = tanhf(o[s]);
+                            if (t != t) atomicExch(P.nan_flag, 1);
+                            P.value256[(size_t)board * 256 + et] = t;
+                        }
+                    }
+                }
+            }
+            // ---- softmax over the 4672 logits of each board (nn.cpp:80), one warp per board ----
+            epi_bar();
+            if (e < NB) {
+                const int board = item * NB + e;
+                float* lg = reinterpret_cast<float*>(region) + (size_t)e * KB_PSIZE;
+                float m = -INFINITY;
+                for (int i = lane; i < KB_PSIZE; i += 32) m = fmaxf(m, lg[i]);
+                for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                float sum = 0.0f;
+                for (int i = lane; i < KB_PSIZE; i += 32) {
+                    const float ex = expf(lg[i] - m);
+                    lg[i] = ex;
+                    sum += ex;
+                }
+                for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                const float inv = 1.0f / sum;
+                if (board < P.boards) {
+                    float* out = P.policy + (size_t)board * KB_PSIZE;
+                    bool bad = false;
+                    for (int i = lane; i < KB_PSIZE; i += 32) {
+                        const float o = lg[i] * inv;
+                        bad |= (o != o);
+                        out[i] = o;
+                    }
+                    if (bad) atomicExch(P.nan_flag, 1);
+                }
+            }
+            epi_bar();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 // valueconv 1x1 (F -> 1) + BN + ReLU, Linear(64 -> 256), tanh (nn.cpp:83-88).  One block per
 // board.  wv / bv: BN-folded conv weights; fct: valuefc.weight transposed to [64][256].
 __global__ void __launch_bounds__(256) k_value_head(const uint4* x, int chunks, int boards, const float* wv, float bv, const float* fct,
@@ -354,6 +663,8 @@ struct Layer {
     int cin_chunks, slice, n_tile, n_total, n_valid, ntaps, relu;
     uint4* w = nullptr;
     float* bias = nullptr;
+    std::vector<uint16_t> hw;   // host copy of the packed weights (fused-kernel concatenation)
+    std::vector<float> hbias;
 };
 
 uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
@@ -379,6 +690,11 @@ struct kb_net {
     float *obs_dev = nullptr, *pol_dev = nullptr, *val_dev = nullptr;
     int stage_cap = 0;
     int launches = 0;
+    // fused single-kernel path (filters == 64)
+    bool fused = false;
+    kb::FusedParams fp;
+    uint4* fused_w = nullptr;
+    float* fused_bias = nullptr;
 };
 
 namespace kb {
@@ -405,7 +721,7 @@ int net_reserve(kb_net* net, int batch) {
     return KB_OK;
 }
 void* net_input_planes(kb_net* net) { return net->P; }
-int net_launches_per_forward(kb_net* net) { return (int)net->layers.size() + 2; }
+int net_launches_per_forward(kb_net* net) { return net->fused ? 1 : (int)net->layers.size() + 2; }
 
 template <int N_TILE, int SLICE>
 static int launch_conv(const ConvParams& p, cudaStream_t st) {
@@ -454,6 +770,24 @@ int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_
     int r = net_reserve(net, batch);
     if (r) return r;
     const uint4* in = reinterpret_cast<const uint4*>(planes);
+    if (net->fused) {
+        static bool configured = false;
+        if (!configured) {
+            KB_CUDA(cudaFuncSetAttribute(k_tower64, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
+            configured = true;
+        }
+        FusedParams fp = net->fp;
+        fp.planes = in;
+        fp.policy = policy_dev;
+        fp.value256 = value256_dev;
+        fp.nan_flag = net->nan_flag;
+        fp.items = items_for(batch);
+        fp.boards = batch;
+        const int grid = fp.items < sm_count() ? fp.items : sm_count();
+        k_tower64<<<grid, 384, FZ_SMEM, st>>>(fp);
+        KB_CUDA(cudaGetLastError());
+        return KB_OK;
+    }
     size_t li = 0;
     if ((r = run_conv(net->layers[li++], in, net->X, nullptr, nullptr, batch, st))) return r;
     for (int i = 0; i < net->residuals; ++i) {
@@ -524,6 +858,8 @@ int pack_conv(Layer& L, const float* w, const float* b, int O, int Cin, int k, c
     KB_CUDA(cudaMemcpy(L.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     KB_CUDA(cudaMalloc(&L.bias, bias.size() * 4));
     KB_CUDA(cudaMemcpy(L.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    L.hw.swap(packed);
+    L.hbias.swap(bias);
     return KB_OK;
 }
 
@@ -554,6 +890,7 @@ int kb_net_destroy(kb_net* n) {
     cudaFree(n->wv); cudaFree(n->fct); cudaFree(n->fcb);
     cudaFree(n->P); cudaFree(n->X); cudaFree(n->Y); cudaFree(n->H);
     cudaFree(n->nan_flag); cudaFree(n->obs_dev); cudaFree(n->pol_dev); cudaFree(n->val_dev);
+    cudaFree(n->fused_w); cudaFree(n->fused_bias);
     delete n;
     return KB_OK;
 }
@@ -633,6 +970,66 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         KB_CUDA(cudaMemcpy(net->wv, wv.data(), F * 4, cudaMemcpyHostToDevice));
         KB_CUDA(cudaMemcpy(net->fct, fct.data(), 64 * 256 * 4, cudaMemcpyHostToDevice));
         KB_CUDA(cudaMemcpy(net->fcb, fb, 256 * 4, cudaMemcpyHostToDevice));
+    }
+    // fused single-kernel path: 64 filters, biases fit the kernel's shared-memory table
+    net->fused = false;
+    cudaFree(net->fused_w);
+    cudaFree(net->fused_bias);
+    net->fused_w = nullptr;
+    net->fused_bias = nullptr;
+    const char* nofuse = getenv("KB_NO_FUSED_TOWER");
+    if (F == 64 && R <= 6 && !(nofuse && nofuse[0] == '1')) {
+        std::vector<uint16_t> allw;
+        std::vector<float> allb;
+        FusedParams& fp = net->fp;
+        memset(&fp, 0, sizeof(fp));
+        const int XOFF = 0, YOFF = 8 * PLANE_BYTES;
+        fp.n_layers = (int)net->layers.size();
+        fp.tower_layers = 1 + 2 * R;
+        for (int l = 0; l < fp.n_layers; ++l) {
+            const Layer& L = net->layers[l];
+            FusedLayer& f = fp.layer[l];
+            f.chunks_in = L.cin_chunks;
+            f.n = L.n_total;
+            f.ntaps = L.ntaps;
+            f.relu = L.relu;
+            f.skip = 0;
+            f.kind = 0;
+            f.bias_off = (int)allb.size();
+            f.idesc = ptx::idesc_bf16(128, L.n_total);
+            if (l == 0) {                       // conv1: P (parked in Y) -> X
+                f.src_off = YOFF;
+                f.dst_off = XOFF;
+            } else if (l < fp.tower_layers) {
+                const bool first = (l - 1) % 2 == 0;  // residual conv1: X -> Y, conv2: Y -> X (+skip)
+                f.src_off = first ? XOFF : YOFF;
+                f.dst_off = first ? YOFF : XOFF;
+                f.skip = first ? 0 : 1;
+            } else if (l == fp.tower_layers) {  // policyconv: X -> H (overlays X|Y)
+                f.src_off = XOFF;
+                f.dst_off = 0;
+            } else {                            // policyconv2: H -> fp32 logits
+                f.src_off = 0;
+                f.dst_off = 0;
+                f.kind = 1;
+            }
+            allw.insert(allw.end(), L.hw.begin(), L.hw.end());
+            allb.insert(allb.end(), L.hbias.begin(), L.hbias.end());
+        }
+        fp.n_bias = (int)allb.size();
+        if (fp.n_bias <= 1400 && fp.n_layers <= 16) {
+            KB_CUDA(cudaMalloc(&net->fused_w, allw.size() * 2));
+            KB_CUDA(cudaMemcpy(net->fused_w, allw.data(), allw.size() * 2, cudaMemcpyHostToDevice));
+            KB_CUDA(cudaMalloc(&net->fused_bias, allb.size() * 4));
+            KB_CUDA(cudaMemcpy(net->fused_bias, allb.data(), allb.size() * 4, cudaMemcpyHostToDevice));
+            fp.w = net->fused_w;
+            fp.bias = net->fused_bias;
+            fp.wv = net->wv;
+            fp.fct = net->fct;
+            fp.fcb = net->fcb;
+            fp.bv = net->bv;
+            net->fused = true;
+        }
     }
     net->loaded = true;
     return KB_OK;

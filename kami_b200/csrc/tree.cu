@@ -427,44 +427,65 @@ __device__ bool push_once(const PoolDev& P, int t, int action) {
         c.depth = 0;
     }
     __syncwarp();
-    if (c.alloc > P.cap / 2) compact_into_other_space(P, t, keep);
+    // Re-rooting is free (the root index moves); the copying collector only runs when the arena
+    // could not hold another move's worth of expansions.
+    const u32 reserve = P.cfg.selfplay_nodes > 0 && (u32)P.cfg.selfplay_nodes * 64u < P.cap / 2 ? (u32)P.cfg.selfplay_nodes * 64u : P.cap / 2;
+    if (c.alloc + reserve > P.cap) compact_into_other_space(P, t, keep);
     else if (lane == 0) c.root = keep;
     __syncwarp();
     return true;
 }
 
-// MCTS::pick (mcts.h:137-184); u01 stands in for rand()/RAND_MAX.
-__device__ int pick_once(const PoolDev& P, int t, float alpha, double u01) {
+// MCTS::pick (mcts.h:137-184); u01 stands in for rand()/RAND_MAX.  The pow() calls run one per
+// lane; the double-precision sums stay sequential in list order like the reference's loops.
+__device__ int pick_once(const PoolDev& P, int t, float alpha, double u01, WarpScratch& s) {
     TreeCtl& c = P.ctl[t];
     const Node* nodes = tree_nodes(P, t, c.space);
     const u32* meta = tree_meta(P, t, c.space);
     const int k = (int)(meta[c.root] >> 16);
     const u32 c0 = nodes[c.root].child0;
+    const int lane = lane_id();
     if (k == 0) return -2;
     int result = -1;
-    if (lane_id() == 0) {
-        if (alpha < 0.1f) {
-            int bn = 0;
-            for (int i = 0; i < k; ++i)
-                if (nodes[c0 + i].n > bn) {
-                    bn = nodes[c0 + i].n;
-                    result = (int)(meta[c0 + i] & 0xFFFF);
-                }
-        } else {
-            const double e = (double)__fdiv_rn(1.0f, alpha);
-            double len = 0.0;
-            for (int i = 0; i < k; ++i) len += pow((double)nodes[c0 + i].n, e);
-            double ind = u01;
-            result = (int)(meta[c0 + k - 1] & 0xFFFF);
-            for (int i = 0; i < k; ++i) {
-                ind -= pow((double)nodes[c0 + i].n, e) / len;
-                if (ind <= 0.0) {
-                    result = (int)(meta[c0 + i] & 0xFFFF);
-                    break;
-                }
+    if (alpha < 0.1f) {
+        int bn = 0, bi = 0x7fffffff;
+        for (int i = lane; i < k; i += 32) {
+            const int n = nodes[c0 + i].n;
+            if (n > bn) {  // strict >: the first maximum wins
+                bn = n;
+                bi = i;
             }
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int on = __shfl_xor_sync(0xffffffffu, bn, off), oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (on > bn || (on == bn && oi < bi)) {
+                bn = on;
+                bi = oi;
+            }
+        }
+        if (bn > 0) result = (int)(meta[c0 + bi] & 0xFFFF);  // (Q15) -1 when every child has n == 0
+        return result;
     }
+    double* dist = reinterpret_cast<double*>(s.score);  // 128 doubles over score[] + sorted_mv[] (1 KB)
+    const double e = (double)__fdiv_rn(1.0f, alpha);
+    for (int i = lane; i < k && i < MAX_MOVES; i += 32) dist[i] = pow((double)nodes[c0 + i].n, e);
+    __syncwarp();
+    if (lane == 0) {
+        double len = 0.0;
+        for (int i = 0; i < k; ++i) len += dist[i];
+        double ind = u01;
+        int pi = k - 1;
+        for (int i = 0; i < k; ++i) {
+            ind -= dist[i] / len;
+            if (ind <= 0.0) {
+                pi = i;
+                break;
+            }
+        }
+        result = (int)(meta[c0 + pi] & 0xFFFF);
+    }
+    __syncwarp();
     return __shfl_sync(0xffffffffu, result, 0);
 }
 
@@ -510,7 +531,7 @@ __device__ void play_move(const PoolDev& P, int t, WarpScratch& s) {
     float alpha = P.cfg.alpha_final;  // selfplay.cpp:153-156
     if (ply < P.cfg.alpha_cutoff) alpha = (float)(pow((double)P.cfg.alpha_decay, (double)ply) * (double)P.cfg.alpha_initial);
     const double u = u01_from(splitmix(c.rng ^ 0xA5A5A5A5DEADBEEFULL));
-    const int action = pick_once(P, t, alpha, u);
+    const int action = pick_once(P, t, alpha, u, s);
     if (action < 0) {
         raise(P, KB_ERR_NO_CHILD);
         return;
@@ -612,7 +633,8 @@ __global__ void k_tree_expand(PoolDev P, int t, const float* policy, float value
     expand_once(P, t, policy, value, disable_bootstrap != 0, s);
 }
 __global__ void k_tree_pick(PoolDev P, int t, float alpha, double u01, int* out) {
-    const int a = pick_once(P, t, alpha, u01);
+    __shared__ WarpScratch s;
+    const int a = pick_once(P, t, alpha, u01, s);
     if (lane_id() == 0) *out = a;
 }
 __global__ void k_tree_push(PoolDev P, int t, int action) { push_once(P, t, action); }

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 
 #include "chess.cuh"
 
@@ -96,12 +97,15 @@ struct PoolDev {
 };
 
 struct WarpScratch {
-    MoveList ml;
-    int score[MAX_MOVES];
+    // score[] (512 B) + sorted_mv[] (256 B) + sorted_ok[] (128 B) + fbuf head are also viewed as
+    // 128 doubles by pick_once, so they stay first, contiguous and 8-byte aligned
+    alignas(8) int score[MAX_MOVES];
     u16 sorted_mv[MAX_MOVES];
     u8 sorted_ok[MAX_MOVES];
     float fbuf[MAX_MOVES];
     u16 tmp_out[MAX_MOVES];
+    MoveList ml;
 };
+static_assert(offsetof(WarpScratch, fbuf) + sizeof(float) * MAX_MOVES >= sizeof(double) * MAX_MOVES, "pick_once scratch view");
 
 }  // namespace kb

@@ -232,7 +232,11 @@ def test_conv1_layer_exact_structure(kb):
     F = 64
     params = NO.init_params(F, 0, seed=5)
     net = kb.NN(F, 0)
-    net.load_blob(NO.pack_blob(params, F, 0))
+    os.environ["KB_NO_FUSED_TOWER"] = "1"  # per-layer kernels keep activations in global memory
+    try:
+        net.load_blob(NO.pack_blob(params, F, 0))
+    finally:
+        del os.environ["KB_NO_FUSED_TOWER"]
     envs = H.sample_positions(9, seed=8)
     obs = np.stack([e.observe() for e in envs])
     net.forward_full(obs)
@@ -264,6 +268,24 @@ def test_net_golden_reference_outputs(kb):
 @pytest.mark.parametrize("F,R,B", [(64, 2, 256), (256, 2, 64), (128, 1, 20)])
 def test_net_vs_oracle(kb, F, R, B):
     _check_net(kb, F, R, B, seed=12)
+
+
+def test_net_fused_kernel_matches_per_layer_kernels(kb):
+    """filters == 64 runs as ONE fused kernel (k_tower64); the per-layer kernels (k_conv + heads)
+    must give the same network."""
+    params = NO.init_params(64, 2, seed=21)
+    blob = NO.pack_blob(params, 64, 2)
+    fused, layered = kb.NN(64, 2), kb.NN(64, 2)
+    fused.load_blob(blob)
+    os.environ["KB_NO_FUSED_TOWER"] = "1"
+    try:
+        layered.load_blob(blob)
+    finally:
+        del os.environ["KB_NO_FUSED_TOWER"]
+    obs = np.stack([e.observe() for e in H.sample_positions(300, seed=30)])
+    pf, vf = fused.forward_full(obs)
+    pl, vl = layered.forward_full(obs)
+    assert np.abs(vf - vl).max() < 1e-5 and np.abs(pf - pl).max() < 1e-6
 
 
 def test_net_batch_edges(kb):
