@@ -120,23 +120,15 @@ def barrier(dist, local):
 
 
 def reduce_max(dist, local, x):
-    if dist is None:
-        return x
-    import torch
+    from kami_b200.parallel import Reducer
 
-    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    return Reducer(dist, "cuda:%d" % local).max(x)
 
 
 def reduce_sum(dist, local, x):
-    if dist is None:
-        return x
-    import torch
+    from kami_b200.parallel import Reducer
 
-    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    return Reducer(dist, "cuda:%d" % local).sum(x)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -274,6 +266,7 @@ def run_ours(args, rank, world, local, dist):
     import kami_b200
     import nn_oracle as NO
     from kami_b200 import api
+    from kami_b200.parallel import per_rank_seed
 
     api.init(local)
     L = kami_b200.lib()
@@ -283,7 +276,7 @@ def run_ours(args, rank, world, local, dist):
     net.load_blob(NO.pack_blob(NO.init_params(FILTERS, RESIDUALS, seed=1), FILTERS, RESIDUALS))
     kw = dict(noise_weight=0.05, selfplay_nodes=SELFPLAY_NODES, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5,
               alpha_cutoff=20, draw_value_pct=50, **H.DEF_YML)
-    pool = kami_b200.TreePool(TREES_PER_GPU, NODE_CAPACITY, api.tree_cfg(seed=1000 + rank, **kw))
+    pool = kami_b200.TreePool(TREES_PER_GPU, NODE_CAPACITY, api.tree_cfg(seed=per_rank_seed(1000, rank), **kw))
 
     def timed_steps(fn, k):
         ms = C.c_float()
