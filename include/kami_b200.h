@@ -107,6 +107,8 @@ size_t kb_net_planes_bytes(int batch);
 int kb_net_flops(kb_net* net, double* tower_flops, double* heads_flops); /* per position */
 /* test hook: one board of an internal activation tensor as fp32 [channels][64] */
 int kb_net_debug_activation(kb_net* net, int which, int board, float* out, int* channels);
+/* profiling hook: clock64 stamps of the fused tower kernel's phases (CTA 0) */
+int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, int* count);
 
 /* ---- MCTS: kami/mcts.h:15-349; Selfplay::inference_main kami/selfplay.cpp:58-213 ---------- */
 typedef struct kb_tree_cfg {

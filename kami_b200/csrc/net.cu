@@ -25,43 +25,46 @@
 namespace kb {
 
 struct ConvParams {
-    const uint4* in;    // input activations, chunks_in planes per item
-    uint4* out;         // bf16 output activations (tall image) or nullptr
+    const uint4* in;    // input activations, slabs_in 64-channel slabs per item
+    uint4* out;         // bf16 output activations (swizzled tall image) or nullptr
     const uint4* skip;  // residual input added after the ReLU (nn.cpp:31), or nullptr
     float* out_f32;     // dense fp32 [boards][64][n_valid] output (policy logits) or nullptr
-    const uint4* w;     // weights, one contiguous block per (pass, k-slice, tap)
+    const uint4* w;     // weights, one contiguous block per (pass, slab, tap)
     const float* bias;  // folded bias, n_total entries
     int items, boards;
-    int chunks_in, chunks_out;
+    int slabs_in, slabs_out;
+    int ksteps;   // 16-channel MMA steps per slab: 4, or 2 for the 30(32)-channel input slab
     int n_total;  // padded output channels (multiple of N_TILE)
     int n_valid;  // real output channels
     int ntaps;    // 9 (3x3, pad 1) or 1 (1x1)
     int relu;
 };
 
-template <int N_TILE, int SLICE>
+template <int N_TILE>
 struct ConvCfg {
-    static constexpr int MT = 4;                      // 4 M tiles x 16 tall rows = the 64 rows of an item
-    static constexpr int KSTEPS = SLICE / 2;          // one MMA covers K = 16 = two 8-channel planes
-    static constexpr int A_BYTES = SLICE * PLANE_BYTES;
-    static constexpr int B_BYTES = SLICE * N_TILE * 16;
+    static constexpr int MT = 4;                       // 4 M tiles x 16 tall rows = the 64 rows of an item
+    static constexpr int A_BYTES = SLAB_BYTES;         // one 64-channel slab of an item
+    static constexpr int B_BYTES = N_TILE * LINE_BYTES;  // [n][64 k] swizzled weight block
     static constexpr int NSTAGE = 4;
     static constexpr int ACC_COLS = MT * N_TILE;
     static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int SMEM = BAR_BYTES + 2 * A_BYTES + NSTAGE * B_BYTES;
+    static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;  // stages stay 1024-byte aligned
+    static constexpr int SMEM = BAR_BYTES + 2 * A_BYTES + NSTAGE * B_STRIDE;
     static_assert(ACC_COLS <= 512, "accumulators must fit TMEM");
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(N_TILE % 16 == 0 && N_TILE <= 256, "UMMA N for M=128");
 };
 
-template <int N_TILE, int SLICE>
+// byte offset of tap (dy,dx) for M tile mt inside a slab: first pixel of the tile's first row group
+__device__ __forceinline__ int tap_offset(int mt, int dy, int dx) { return ((16 * mt + dy) * TALL_PITCH + 1 + dx) * LINE_BYTES; }
+
+template <int N_TILE>
 __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
-    using C = ConvCfg<N_TILE, SLICE>;
+    using C = ConvCfg<N_TILE>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = ptx::smem_u32(smem);
-    // barrier map (8 bytes each)
     auto b_full = [&](int s) { return bar0 + 8u * s; };
     auto b_empty = [&](int s) { return bar0 + 8u * (4 + s); };
     auto a_full = [&](int s) { return bar0 + 8u * (8 + s); };
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     const uint32_t a_smem = bar0 + C::BAR_BYTES;
     const uint32_t b_smem = a_smem + 2 * C::A_BYTES;
 
-    const int kslices = P.chunks_in / SLICE;
+    const int kslices = P.slabs_in;
     const int npass = P.n_total / N_TILE;
     const int my_items = P.items > (int)blockIdx.x ? (P.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int jobs_per_item = npass * kslices;
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ===== producer: bulk TMA copies of activation slices (A) and weight blocks (B) =====
+        // ===== producer: bulk TMA copies of activation slabs (A) and weight blocks (B) =====
         auto issue_a = [&](int job) {
             const int ii = job / jobs_per_item, rem = job - ii * jobs_per_item;
             const int ks = rem % kslices;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
             const int buf = job & 1;
             ptx::mbar_wait(a_empty(buf), ((job >> 1) & 1) ^ 1);
             ptx::mbar_arrive_expect_tx(a_full(buf), C::A_BYTES);
-            const uint4* src = P.in + ((size_t)item * P.chunks_in + (size_t)ks * SLICE) * PLANE_PIX;
+            const uint4* src = P.in + ((size_t)item * P.slabs_in + ks) * SLAB_U4;
             ptx::bulk_g2s(a_smem + buf * C::A_BYTES, src, C::A_BYTES, a_full(buf));
         };
         if (total_jobs > 0) issue_a(0);
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
                 ptx::mbar_wait(b_empty(stage), sphase ^ 1);
                 ptx::mbar_arrive_expect_tx(b_full(stage), C::B_BYTES);
                 const uint4* src = P.w + ((size_t)(pass * kslices + ks) * P.ntaps + tap) * (C::B_BYTES / 16);
-                ptx::bulk_g2s(b_smem + stage * C::B_BYTES, src, C::B_BYTES, b_full(stage));
+                ptx::bulk_g2s(b_smem + stage * C::B_STRIDE, src, C::B_BYTES, b_full(stage));
                 if (++stage == C::NSTAGE) {
                     stage = 0;
                     sphase ^= 1;
@@ -143,24 +146,26 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
                 ptx::tc_fence_after();
             }
             ptx::mbar_wait(a_full(buf), (job >> 1) & 1);
-            const uint32_t a_base = a_smem + buf * C::A_BYTES;
+            // descriptor words: start addresses advance by plain adds (16-byte units)
+            const uint32_t a_lo0 = ptx::sw128_lo(a_smem + buf * C::A_BYTES);
+            const uint32_t a_hi = ptx::sw128_hi(TALL_PITCH * LINE_BYTES), b_hi = ptx::sw128_hi(1024);
             const uint32_t d_base = tmem_base + acc * C::ACC_COLS;
+            const int ksteps = P.ksteps;
             for (int tap = 0; tap < P.ntaps; ++tap) {
                 const int dy = P.ntaps == 9 ? tap / 3 - 1 : 0, dx = P.ntaps == 9 ? tap % 3 - 1 : 0;
+                const uint32_t a_tap = a_lo0 + (uint32_t)((dy * TALL_PITCH + dx + 1) * (LINE_BYTES / 16));
                 ptx::mbar_wait(b_full(stage), sphase);
                 ptx::tc_fence_after();
-                const uint32_t b_base = b_smem + stage * C::B_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < C::KSTEPS; ++kk) {
-                    const uint64_t bdesc = ptx::smem_desc(b_base + kk * 2 * (N_TILE * 16), N_TILE * 16, 128);
+                const uint32_t b_lo0 = ptx::sw128_lo(b_smem + stage * C::B_STRIDE);
+                uint32_t first = (ks | tap) == 0 ? 0u : 1u;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
 #pragma unroll
                     for (int mt = 0; mt < C::MT; ++mt) {
-                        const int px = (16 * mt + dy) * TALL_PITCH + 1 + dx;  // may be negative for mt = 0, dy = -1
-                        const uint32_t a_addr = (uint32_t)((int)(a_base + kk * 2 * PLANE_BYTES) + px * 16);
-                        const uint64_t adesc = ptx::smem_desc(a_addr, PLANE_BYTES, TALL_PITCH * 16);
-                        const uint32_t accumulate = (ks | tap | kk) != 0;
-                        ptx::mma_bf16(d_base + mt * N_TILE, adesc, bdesc, idesc, accumulate);
+                        const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * (16 * TALL_PITCH * LINE_BYTES / 16), a_hi);
+                        ptx::mma_bf16(d_base + mt * N_TILE, adesc, bdesc, idesc, first);
                     }
+                    first = 1u;
                 }
                 ptx::mma_commit(b_empty(stage));
                 if (++stage == C::NSTAGE) {
@@ -195,46 +200,54 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
                     const int board = item * NB + slot;
                     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * C::ACC_COLS + mt * N_TILE;
 #pragma unroll 1
-                    for (int cg = 0; cg < N_TILE / 16; ++cg) {
-                        uint32_t v[16];
-                        ptx::tmem_ld16(taddr + cg * 16, v);
+                    for (int cg2 = 0; cg2 < N_TILE / 16; cg2 += 2) {
+                        // two column groups (32 fp32 columns) per round trip to TMEM
+                        uint32_t v[2][16];
+                        ptx::tmem_ld16(taddr + cg2 * 16, v[0]);
+                        if (cg2 + 1 < N_TILE / 16) ptx::tmem_ld16(taddr + (cg2 + 1) * 16, v[1]);
                         ptx::tmem_ld_wait();
-                        const int ch0 = pass * N_TILE + cg * 16;
-                        float f[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            f[j] = __uint_as_float(v[j]) + __ldg(P.bias + ch0 + j);
-                            if (P.relu) f[j] = fmaxf(f[j], 0.0f);
-                        }
                         if (!valid) continue;
-                        if (P.out_f32) {
-                            if (board < P.boards) {
-                                float* dst = P.out_f32 + ((size_t)board * 64 + (y * 8 + x)) * P.n_valid;
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (ch0 + j < P.n_valid) dst[ch0 + j] = f[j];
+                        for (int g = 0; g < 2; ++g) {
+                            const int cg = cg2 + g;
+                            if (cg >= N_TILE / 16) break;
+                            const int ch0 = pass * N_TILE + cg * 16;
+                            float f[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                f[j] = __uint_as_float(v[g][j]) + __ldg(P.bias + ch0 + j);
+                                if (P.relu) f[j] = fmaxf(f[j], 0.0f);
                             }
-                        } else {
+                            if (P.out_f32) {
+                                if (board < P.boards) {
+                                    float* dst = P.out_f32 + ((size_t)board * 64 + (y * 8 + x)) * P.n_valid;
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const size_t idx = ((size_t)item * P.chunks_out + (ch0 >> 3) + h) * PLANE_PIX + px;
-                                if (P.skip) {
-                                    const uint4 s4 = P.skip[idx];
-                                    const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&s4);
+                                    for (int j = 0; j < 16; ++j)
+                                        if (ch0 + j < P.n_valid) dst[ch0 + j] = f[j];
+                                }
+                            } else {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const int ch = ch0 + 8 * h;  // first of 8 channels
+                                    const size_t idx = ((size_t)item * P.slabs_out + (ch >> 6)) * SLAB_U4 + chunk_u4(px, (ch >> 3) & 7);
+                                    if (P.skip) {
+                                        const uint4 s4 = P.skip[idx];
+                                        const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&s4);
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            const float2 sv = __bfloat1622float2(sb[k]);
+                                            f[h * 8 + 2 * k] += sv.x;
+                                            f[h * 8 + 2 * k + 1] += sv.y;
+                                        }
+                                    }
+                                    uint32_t w4[4];
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
-                                        const float2 sv = __bfloat1622float2(sb[k]);
-                                        f[h * 8 + 2 * k] += sv.x;
-                                        f[h * 8 + 2 * k + 1] += sv.y;
+                                        const __nv_bfloat162 b = __floats2bfloat162_rn(f[h * 8 + 2 * k], f[h * 8 + 2 * k + 1]);
+                                        w4[k] = *reinterpret_cast<const uint32_t*>(&b);
                                     }
+                                    P.out[idx] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                                 }
-                                uint32_t w4[4];
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const __nv_bfloat162 b = __floats2bfloat162_rn(f[h * 8 + 2 * k], f[h * 8 + 2 * k + 1]);
-                                    w4[k] = *reinterpret_cast<const uint32_t*>(&b);
-                                }
-                                P.out[idx] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                             }
                         }
                     }
@@ -250,24 +263,25 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-
 // ------------------------------------------------------------------------------------------
 // Fused forward for the 64-filter network (options.def.yml: filters 64): ONE kernel per batch.
 // A CTA owns an item (7 boards).  Activations never leave shared memory between layers:
 //
-//   region  = [ X : 8 planes | Y : 8 planes ]   (160 KB, tall-image planes, pads zero)
-//   P (input, 4 planes) lands in Y; conv1: P -> X; residual r: X -> Y -> X (+skip from X);
-//   value head (CUDA cores) reads X; policy conv 1x1: X -> H (16 planes, overlays X|Y);
+//   region  = [ X : slab 0 | Y : slab 1 ]   (2 x 80 KB swizzled tall-image slabs, pads zero)
+//   P (input slab) lands in Y; conv1: P -> X; residual r: X -> Y -> X (+skip from X);
+//   value head (CUDA cores) reads X; policy conv 1x1: X -> H (128 ch = both slabs);
 //   policy conv2 1x1: H -> fp32 logits (overlay), softmax over 4672 per board -> global.
 //
-// Warp roles: warp 0 bulk-TMA producer (input planes + all weight blocks in consumption
-// order through a 3-stage ring), warp 1 tcgen05.mma issuer, warp 2 TMEM allocator, warps 4-11
+// Warp roles: warp 0 bulk-TMA producer (input slab + all weight blocks in consumption order
+// through a 5-stage ring), warp 1 tcgen05.mma issuer, warp 2 TMEM allocator, warps 4-11
 // epilogue (two warps per TMEM lane quarter, splitting the accumulator columns).
 // ------------------------------------------------------------------------------------------
 struct FusedLayer {
-    int src_off, dst_off;  // byte offsets of the source / destination planes inside the region
-    int chunks_in;         // 8-channel planes read
-    int n;                 // output channels computed (UMMA N)
+    int src_off, dst_off;  // byte offsets of the source / destination slabs inside the region
+    int slabs_in;          // 64-channel slabs read
+    int ksteps;            // 16-channel MMA steps per slab
+    int n;                 // output channels of the layer (accumulator columns per M tile)
+    int n_sub;             // UMMA N of one weight block (n = nsub * n_sub)
     int ntaps, relu, skip, bias_off;
     int kind;              // 0 bf16 activation to smem, 1 fp32 logits to smem
     uint32_t idesc;
@@ -282,17 +296,19 @@ struct FusedParams {
     const float* fct;
     const float* fcb;
     int* nan_flag;
+    long long* ts;  // optional per-phase clock64 stamps of CTA 0 (profiling hook), or nullptr
     float bv;
     int n_bias, items, boards, n_layers, tower_layers;
     FusedLayer layer[16];
 };
 constexpr int FZ_HDR = 8192;                  // barriers, tmem slot, value scratch, biases
-constexpr int FZ_REGION = 16 * PLANE_BYTES;   // 163840
-constexpr int FZ_STAGE = 16384;
-constexpr int FZ_NSTAGE = 3;
+constexpr int FZ_REGION = 2 * SLAB_BYTES;     // 163840
+constexpr int FZ_STAGE = 10240;               // one weight block: n_sub x 128 B <= 10 KB (80 rows)
+constexpr int FZ_NSTAGE = 5;                  // 50 KB of weights in flight
 constexpr int FZ_SMEM = FZ_HDR + FZ_REGION + FZ_NSTAGE * FZ_STAGE;
 constexpr int FZ_EPI_THREADS = 256;
 static_assert(FZ_SMEM <= 232448, "fused tower shared memory budget");
+static_assert(FZ_STAGE % 1024 == 0 && FZ_HDR % 1024 == 0, "swizzled operands need 1024-byte aligned bases");
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -302,8 +318,8 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s0 = ptx::smem_u32(smem);
     auto b_full = [&](int s) { return s0 + 8u * s; };
-    auto b_empty = [&](int s) { return s0 + 8u * (4 + s); };
-    const uint32_t p_full = s0 + 8u * 8, t_full = s0 + 8u * 9, act_ready = s0 + 8u * 10, region_clean = s0 + 8u * 11;
+    auto b_empty = [&](int s) { return s0 + 8u * (8 + s); };
+    const uint32_t p_full = s0 + 8u * 16, t_full = s0 + 8u * 17, act_ready = s0 + 8u * 18, region_clean = s0 + 8u * 19;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
     float* vbuf = reinterpret_cast<float*>(smem + 512);     // [7][64] value-conv outputs
     float* sbias = reinterpret_cast<float*>(smem + 2560);   // all folded biases
@@ -340,14 +356,13 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             ptx::mbar_wait(region_clean, ii & 1);
-            ptx::mbar_arrive_expect_tx(p_full, IN_CHUNKS * PLANE_BYTES);
-            ptx::bulk_g2s(region_s + 8 * PLANE_BYTES, P.planes + (size_t)item * IN_CHUNKS * PLANE_PIX, IN_CHUNKS * PLANE_BYTES, p_full);
+            ptx::mbar_arrive_expect_tx(p_full, SLAB_BYTES);
+            ptx::bulk_g2s(region_s + SLAB_BYTES, P.planes + (size_t)item * IN_SLABS * SLAB_U4, SLAB_BYTES, p_full);
             const uint4* w = P.w;
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
-                const int slice = L.chunks_in < 8 ? L.chunks_in : 8;
-                const int nblocks = L.ntaps * (L.chunks_in / slice);
-                const uint32_t bytes = (uint32_t)(slice * L.n * 16);
+                const int nblocks = L.slabs_in * L.ntaps * (L.n / L.n_sub);
+                const uint32_t bytes = (uint32_t)(L.n_sub * LINE_BYTES);
                 for (int b = 0; b < nblocks; ++b) {
                     ptx::mbar_wait(b_empty(stage), sphase ^ 1);
                     ptx::mbar_arrive_expect_tx(b_full(stage), bytes);
@@ -373,29 +388,40 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                     act_phase ^= 1;
                 }
                 ptx::tc_fence_after();
-                const int slice = L.chunks_in < 8 ? L.chunks_in : 8;
-                const int kslices = L.chunks_in / slice;
                 const uint32_t a_src = region_s + L.src_off;
-                for (int ks = 0; ks < kslices; ++ks)
-                    for (int tap = 0; tap < L.ntaps; ++tap) {
-                        const int dy = L.ntaps == 9 ? tap / 3 - 1 : 0, dx = L.ntaps == 9 ? tap % 3 - 1 : 0;
-                        ptx::mbar_wait(b_full(stage), sphase);
-                        ptx::tc_fence_after();
-                        const uint32_t b_base = ring_s + stage * FZ_STAGE;
-                        for (int kk = 0; kk < slice / 2; ++kk) {
-                            const uint64_t bdesc = ptx::smem_desc(b_base + kk * 2 * (L.n * 16), L.n * 16, 128);
+                const int nsub = L.n / L.n_sub, ksteps = L.ksteps, ntaps = L.ntaps, n = L.n;
+                const uint32_t idesc = L.idesc;
+                const uint32_t a_hi = ptx::sw128_hi(TALL_PITCH * LINE_BYTES), b_hi = ptx::sw128_hi(1024);
+                // weight blocks arrive in the order (sub-block, slab, tap)
+                for (int sub = 0; sub < nsub; ++sub)
+                    for (int ks = 0; ks < L.slabs_in; ++ks) {
+                        const uint32_t a_lo0 = ptx::sw128_lo(a_src + ks * SLAB_BYTES);
+                        const uint32_t d_base = tmem_base + sub * L.n_sub;
+                        int dy = ntaps == 9 ? -1 : 0, dx = ntaps == 9 ? -1 : 0;
+                        for (int tap = 0; tap < ntaps; ++tap) {
+                            const uint32_t a_tap = a_lo0 + (uint32_t)((dy * TALL_PITCH + dx + 1) * (LINE_BYTES / 16));
+                            ptx::mbar_wait(b_full(stage), sphase);
+                            ptx::tc_fence_after();
+                            const uint32_t b_lo0 = ptx::sw128_lo(ring_s + stage * FZ_STAGE);
+                            uint32_t first = (ks | tap) == 0 ? 0u : 1u;
+                            for (int kk = 0; kk < ksteps; ++kk) {
+                                const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
 #pragma unroll
-                            for (int mt = 0; mt < 4; ++mt) {
-                                const int px = (16 * mt + dy) * TALL_PITCH + 1 + dx;
-                                const uint32_t a_addr = (uint32_t)((int)(a_src + (ks * 8 + kk * 2) * PLANE_BYTES) + px * 16);
-                                const uint64_t adesc = ptx::smem_desc(a_addr, PLANE_BYTES, TALL_PITCH * 16);
-                                ptx::mma_bf16(tmem_base + mt * L.n, adesc, bdesc, L.idesc, (ks | tap | kk) != 0);
+                                for (int mt = 0; mt < 4; ++mt) {
+                                    const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * (16 * TALL_PITCH * LINE_BYTES / 16), a_hi);
+                                    ptx::mma_bf16(d_base + mt * n, adesc, bdesc, idesc, first);
+                                }
+                                first = 1u;
                             }
-                        }
-                        ptx::mma_commit(b_empty(stage));
-                        if (++stage == FZ_NSTAGE) {
-                            stage = 0;
-                            sphase ^= 1;
+                            ptx::mma_commit(b_empty(stage));
+                            if (++stage == FZ_NSTAGE) {
+                                stage = 0;
+                                sphase ^= 1;
+                            }
+                            if (++dx > 1) {
+                                dx = -1;
+                                ++dy;
+                            }
                         }
                     }
                 ptx::mma_commit(t_full);
@@ -409,6 +435,10 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
         const int e = warp - 4, q = e & 3, half = e >> 2;
         const int et = threadIdx.x - 128;  // 0..255
         uint32_t t_phase = 0;
+        const bool stamp = P.ts && blockIdx.x == 0 && et == 0;
+        int nts = 0;
+#define KB_STAMP() do { if (stamp && nts < 60) P.ts[nts++] = clock64(); } while (0)
+        KB_STAMP();
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             {   // pads must read as zero: clear the whole region, then hand it to the async proxy
@@ -419,11 +449,13 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(region_clean);
             }
+            KB_STAMP();
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
                 ptx::mbar_wait(t_full, t_phase);
                 t_phase ^= 1;
                 ptx::tc_fence_after();
+                KB_STAMP();
                 if (l == P.tower_layers) epi_bar();  // every warp finished reading X for the value head
                 const int ncg = L.n / 16;
                 const int cg0 = half == 0 ? 0 : (ncg + 1) / 2, cg1 = half == 0 ? (ncg + 1) / 2 : ncg;
@@ -435,17 +467,30 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                     const bool valid = R >= 1 && y < 8 && slot < NB;
                     const int px = R * TALL_PITCH + 1 + x;
                     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + mt * L.n;
-#pragma unroll 1
-                    for (int cg = cg0; cg < cg1; ++cg) {
-                        uint32_t v[16];
-                        ptx::tmem_ld16(taddr + cg * 16, v);
-                        ptx::tmem_ld_wait();
-                        if (!valid) continue;
-                        float f[16];
+                    // up to 4 column groups (64 fp32 columns) per warp and tile: issue every TMEM load, wait once
+                    uint32_t v[4][16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            f[j] = __uint_as_float(v[j]) + sbias[L.bias_off + cg * 16 + j];
-                            if (L.relu) f[j] = fmaxf(f[j], 0.0f);
+                    for (int g = 0; g < 4; ++g)
+                        if (cg0 + g < cg1) ptx::tmem_ld16(taddr + (cg0 + g) * 16, v[g]);
+                    ptx::tmem_ld_wait();
+                    if (!valid) continue;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int cg = cg0 + g;
+                        if (cg >= cg1) break;
+                        float f[16];
+                        const float4* b4 = reinterpret_cast<const float4*>(sbias + L.bias_off + cg * 16);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 bb = b4[j];
+                            f[4 * j + 0] = __uint_as_float(v[g][4 * j + 0]) + bb.x;
+                            f[4 * j + 1] = __uint_as_float(v[g][4 * j + 1]) + bb.y;
+                            f[4 * j + 2] = __uint_as_float(v[g][4 * j + 2]) + bb.z;
+                            f[4 * j + 3] = __uint_as_float(v[g][4 * j + 3]) + bb.w;
+                        }
+                        if (L.relu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
                         }
                         if (L.kind == 1) {
                             float* lg = reinterpret_cast<float*>(region) + (size_t)slot * KB_PSIZE + (y * 8 + x) * 73;
@@ -455,7 +500,8 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                         } else {
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
-                                uint4* dst = reinterpret_cast<uint4*>(region + L.dst_off) + (size_t)(cg * 2 + h) * PLANE_PIX + px;
+                                const int ch = cg * 16 + 8 * h;
+                                uint4* dst = reinterpret_cast<uint4*>(region + L.dst_off) + (size_t)(ch >> 6) * SLAB_U4 + chunk_u4(px, (ch >> 3) & 7);
                                 if (L.skip) {  // x = skip + relu(...), the skip is the destination itself (nn.cpp:31)
                                     const uint4 s4 = *dst;
                                     const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&s4);
@@ -481,6 +527,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(act_ready);
+                KB_STAMP();
                 if (l == P.tower_layers - 1) {
                     // ---- value head on X (nn.cpp:83-88), overlapping the policy conv's MMAs ----
                     epi_bar();  // X complete
@@ -491,7 +538,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                         float acc = P.bv;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const uint4 a4 = X[c * PLANE_PIX + px];
+                            const uint4 a4 = X[chunk_u4(px, c)];
                             const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&a4);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -524,35 +571,76 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                     }
                 }
             }
-            // ---- softmax over the 4672 logits of each board (nn.cpp:80), one warp per board ----
+            // ---- softmax over the 4672 logits of each board (nn.cpp:80) ----
             epi_bar();
-            if (e < NB) {
-                const int board = item * NB + e;
-                float* lg = reinterpret_cast<float*>(region) + (size_t)e * KB_PSIZE;
-                float m = -INFINITY;
-                for (int i = lane; i < KB_PSIZE; i += 32) m = fmaxf(m, lg[i]);
-                for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                float sum = 0.0f;
-                for (int i = lane; i < KB_PSIZE; i += 32) {
-                    const float ex = expf(lg[i] - m);
-                    lg[i] = ex;
-                    sum += ex;
-                }
-                for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-                const float inv = 1.0f / sum;
-                if (board < P.boards) {
-                    float* out = P.policy + (size_t)board * KB_PSIZE;
-                    bool bad = false;
-                    for (int i = lane; i < KB_PSIZE; i += 32) {
-                        const float o = lg[i] * inv;
-                        bad |= (o != o);
-                        out[i] = o;
+            KB_STAMP();
+            {
+                // every thread owns 19 logits of each of the 7 boards; two block-wide reductions in total
+                float* red = vbuf;  // [8 warps][7] maxima, then [8][7] sums (the value head is done with vbuf)
+                const float* lg = reinterpret_cast<const float*>(region);
+                constexpr int PER = (KB_PSIZE + FZ_EPI_THREADS - 1) / FZ_EPI_THREADS;  // 19
+                float m[NB], sum[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    float mm = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        const int idx = et + i * FZ_EPI_THREADS;
+                        if (idx < KB_PSIZE) mm = fmaxf(mm, lg[b * KB_PSIZE + idx]);
                     }
-                    if (bad) atomicExch(P.nan_flag, 1);
+                    for (int off = 16; off; off >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, off));
+                    if (lane == 0) red[e * NB + b] = mm;
                 }
+                epi_bar();
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    float mm = red[b];
+#pragma unroll
+                    for (int w = 1; w < 8; ++w) mm = fmaxf(mm, red[w * NB + b]);
+                    m[b] = mm;
+                }
+                epi_bar();  // maxima consumed before the sums reuse the scratch
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    float ss = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        const int idx = et + i * FZ_EPI_THREADS;
+                        if (idx < KB_PSIZE) ss += __expf(lg[b * KB_PSIZE + idx] - m[b]);
+                    }
+                    for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                    if (lane == 0) red[e * NB + b] = ss;
+                }
+                epi_bar();
+                bool bad = false;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    float ss = red[b];
+#pragma unroll
+                    for (int w = 1; w < 8; ++w) ss += red[w * NB + b];
+                    sum[b] = ss;
+                    const int board = item * NB + b;
+                    if (board < P.boards) {
+                        const float inv = 1.0f / ss;
+                        float* out = P.policy + (size_t)board * KB_PSIZE;
+#pragma unroll
+                        for (int i = 0; i < PER; ++i) {
+                            const int idx = et + i * FZ_EPI_THREADS;
+                            if (idx < KB_PSIZE) {
+                                const float o = __expf(lg[b * KB_PSIZE + idx] - m[b]) * inv;
+                                bad |= (o != o);
+                                out[idx] = o;
+                            }
+                        }
+                    }
+                }
+                (void)sum;
+                if (bad) atomicExch(P.nan_flag, 1);
             }
             epi_bar();
+            KB_STAMP();
         }
+#undef KB_STAMP
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -561,7 +649,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
 
 // valueconv 1x1 (F -> 1) + BN + ReLU, Linear(64 -> 256), tanh (nn.cpp:83-88).  One block per
 // board.  wv / bv: BN-folded conv weights; fct: valuefc.weight transposed to [64][256].
-__global__ void __launch_bounds__(256) k_value_head(const uint4* x, int chunks, int boards, const float* wv, float bv, const float* fct,
+__global__ void __launch_bounds__(256) k_value_head(const uint4* x, int slabs, int boards, const float* wv, float bv, const float* fct,
                                                      const float* fcb, float* value256, int* nan_flag) {
     __shared__ float part[4][64];
     __shared__ float v[64];
@@ -571,8 +659,8 @@ __global__ void __launch_bounds__(256) k_value_head(const uint4* x, int chunks, 
     const int t = threadIdx.x, pix = t & 63, quarter = t >> 6;
     const int px = tall_pixel(slot, pix);
     float acc = 0.0f;
-    for (int c = quarter; c < chunks; c += 4) {
-        const uint4 a4 = x[((size_t)item * chunks + c) * PLANE_PIX + px];
+    for (int c = quarter; c < slabs * 8; c += 4) {  // c = 8-channel chunk index over all slabs
+        const uint4 a4 = x[((size_t)item * slabs + (c >> 3)) * SLAB_U4 + chunk_u4(px, c & 7)];
         const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&a4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -660,7 +748,7 @@ using namespace kb;
 namespace {
 
 struct Layer {
-    int cin_chunks, slice, n_tile, n_total, n_valid, ntaps, relu;
+    int slabs_in, ksteps, n_tile, n_total, n_valid, ntaps, relu;
     uint4* w = nullptr;
     float* bias = nullptr;
     std::vector<uint16_t> hw;   // host copy of the packed weights (fused-kernel concatenation)
@@ -695,6 +783,7 @@ struct kb_net {
     kb::FusedParams fp;
     uint4* fused_w = nullptr;
     float* fused_bias = nullptr;
+    long long* ts_dev = nullptr;
 };
 
 namespace kb {
@@ -703,16 +792,17 @@ int net_reserve(kb_net* net, int batch) {
     if (batch <= net->cap_boards) return KB_OK;
     cudaStreamSynchronize(main_stream());
     cudaFree(net->P); cudaFree(net->X); cudaFree(net->Y); cudaFree(net->H);
-    const int fc = net->filters / 8;
-    KB_CUDA(cudaMalloc(&net->P, act_bytes(batch, IN_CHUNKS)));
-    KB_CUDA(cudaMalloc(&net->X, act_bytes(batch, fc)));
-    KB_CUDA(cudaMalloc(&net->Y, act_bytes(batch, fc)));
-    KB_CUDA(cudaMalloc(&net->H, act_bytes(batch, 16)));
-    // pad pixels must read as zero forever; epilogues and encoders only ever write board pixels
-    KB_CUDA(cudaMemset(net->P, 0, act_bytes(batch, IN_CHUNKS)));
-    KB_CUDA(cudaMemset(net->X, 0, act_bytes(batch, fc)));
-    KB_CUDA(cudaMemset(net->Y, 0, act_bytes(batch, fc)));
-    KB_CUDA(cudaMemset(net->H, 0, act_bytes(batch, 16)));
+    const int fs = (net->filters + 63) / 64;
+    KB_CUDA(cudaMalloc(&net->P, act_bytes(batch, IN_SLABS)));
+    KB_CUDA(cudaMalloc(&net->X, act_bytes(batch, fs)));
+    KB_CUDA(cudaMalloc(&net->Y, act_bytes(batch, fs)));
+    KB_CUDA(cudaMalloc(&net->H, act_bytes(batch, 2)));
+    // pad pixels (and unused channel chunks) must read as zero forever; epilogues and encoders
+    // only ever write the chunks of board pixels they own
+    KB_CUDA(cudaMemset(net->P, 0, act_bytes(batch, IN_SLABS)));
+    KB_CUDA(cudaMemset(net->X, 0, act_bytes(batch, fs)));
+    KB_CUDA(cudaMemset(net->Y, 0, act_bytes(batch, fs)));
+    KB_CUDA(cudaMemset(net->H, 0, act_bytes(batch, 2)));
     if (!net->nan_flag) {
         KB_CUDA(cudaMalloc(&net->nan_flag, sizeof(int)));
         KB_CUDA(cudaMemset(net->nan_flag, 0, sizeof(int)));
@@ -723,16 +813,16 @@ int net_reserve(kb_net* net, int batch) {
 void* net_input_planes(kb_net* net) { return net->P; }
 int net_launches_per_forward(kb_net* net) { return net->fused ? 1 : (int)net->layers.size() + 2; }
 
-template <int N_TILE, int SLICE>
+template <int N_TILE>
 static int launch_conv(const ConvParams& p, cudaStream_t st) {
-    using C = ConvCfg<N_TILE, SLICE>;
+    using C = ConvCfg<N_TILE>;
     static bool configured = false;
     if (!configured) {
-        KB_CUDA(cudaFuncSetAttribute(k_conv<N_TILE, SLICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        KB_CUDA(cudaFuncSetAttribute(k_conv<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
     const int grid = p.items < sm_count() ? p.items : sm_count();
-    k_conv<N_TILE, SLICE><<<grid, 256, C::SMEM, st>>>(p);
+    k_conv<N_TILE><<<grid, 256, C::SMEM, st>>>(p);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
@@ -747,18 +837,17 @@ static int run_conv(const Layer& L, const uint4* in, uint4* out, const uint4* sk
     p.bias = L.bias;
     p.items = items_for(boards);
     p.boards = boards;
-    p.chunks_in = L.cin_chunks;
-    p.chunks_out = L.n_total / 8;
+    p.slabs_in = L.slabs_in;
+    p.slabs_out = (L.n_total + 63) / 64;
+    p.ksteps = L.ksteps;
     p.n_total = L.n_total;
     p.n_valid = L.n_valid;
     p.ntaps = L.ntaps;
     p.relu = L.relu;
-    if (L.n_tile == 64 && L.slice == 4) return launch_conv<64, 4>(p, st);
-    if (L.n_tile == 64 && L.slice == 8) return launch_conv<64, 8>(p, st);
-    if (L.n_tile == 128 && L.slice == 4) return launch_conv<128, 4>(p, st);
-    if (L.n_tile == 128 && L.slice == 8) return launch_conv<128, 8>(p, st);
-    if (L.n_tile == 80 && L.slice == 8) return launch_conv<80, 8>(p, st);
-    set_error("no conv kernel for n_tile=%d slice=%d", L.n_tile, L.slice);
+    if (L.n_tile == 64) return launch_conv<64>(p, st);
+    if (L.n_tile == 128) return launch_conv<128>(p, st);
+    if (L.n_tile == 80) return launch_conv<80>(p, st);
+    set_error("no conv kernel for n_tile=%d", L.n_tile);
     return KB_ERR_UNSUPPORTED;
 }
 
@@ -781,6 +870,7 @@ int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_
         fp.policy = policy_dev;
         fp.value256 = value256_dev;
         fp.nan_flag = net->nan_flag;
+        fp.ts = net->ts_dev;
         fp.items = items_for(batch);
         fp.boards = batch;
         const int grid = fp.items < sm_count() ? fp.items : sm_count();
@@ -798,7 +888,7 @@ int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_
     if ((r = run_conv(net->layers[li++], net->H, nullptr, nullptr, policy_dev, batch, st))) return r;
     k_softmax<<<batch, 256, 0, st>>>(policy_dev, batch, net->nan_flag);
     KB_CUDA(cudaGetLastError());
-    k_value_head<<<batch, 256, 0, st>>>(net->X, net->filters / 8, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, net->nan_flag);
+    k_value_head<<<batch, 256, 0, st>>>(net->X, (net->filters + 63) / 64, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, net->nan_flag);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
@@ -831,26 +921,27 @@ void fold_bn(const float* g, const float* beta, const float* mean, const float* 
 }
 
 // Packs conv weights [O][Cin][k][k] (scaled per output channel) into the kernel's B layout:
-// blocks ordered (pass, k-slice, tap), each block [chunk in slice][n in tile][8 channels] bf16.
+// blocks ordered (pass, slab, tap); a block is [n in tile][64 input channels] bf16, one 128-byte
+// line per output channel, 128B-swizzled (chunk j of line n at slot j ^ (n & 7)) -- the canonical
+// K-major SWIZZLE_128B operand, copied verbatim into 1024-byte aligned shared memory.
 int pack_conv(Layer& L, const float* w, const float* b, int O, int Cin, int k, const std::vector<float>* scale, const std::vector<float>* shift) {
-    const int kslices = L.cin_chunks / L.slice, npass = L.n_total / L.n_tile, taps = k * k;
-    const size_t block = (size_t)L.slice * L.n_tile * 8;
+    const int kslices = L.slabs_in, npass = L.n_total / L.n_tile, taps = k * k;
+    const size_t block = (size_t)L.n_tile * 64;
     std::vector<uint16_t> packed((size_t)npass * kslices * taps * block, 0);
     for (int pass = 0; pass < npass; ++pass)
         for (int ks = 0; ks < kslices; ++ks)
             for (int tap = 0; tap < taps; ++tap) {
                 uint16_t* dst = packed.data() + ((size_t)(pass * kslices + ks) * taps + tap) * block;
-                for (int c = 0; c < L.slice; ++c)
-                    for (int n = 0; n < L.n_tile; ++n)
-                        for (int e = 0; e < 8; ++e) {
-                            const int o = pass * L.n_tile + n, ci = (ks * L.slice + c) * 8 + e;
-                            float v = 0.0f;
-                            if (o < O && ci < Cin) {
-                                v = w[((size_t)o * Cin + ci) * taps + tap];
-                                if (scale) v *= (*scale)[o];
-                            }
-                            dst[((size_t)c * L.n_tile + n) * 8 + e] = f2bf(v);
+                for (int n = 0; n < L.n_tile; ++n)
+                    for (int c = 0; c < 64; ++c) {
+                        const int o = pass * L.n_tile + n, ci = ks * 64 + c;
+                        float v = 0.0f;
+                        if (o < O && ci < Cin) {
+                            v = w[((size_t)o * Cin + ci) * taps + tap];
+                            if (scale) v *= (*scale)[o];
                         }
+                        dst[(size_t)n * 64 + (((c >> 3) ^ (n & 7)) << 3) + (c & 7)] = f2bf(v);
+                    }
             }
     std::vector<float> bias(L.n_total, 0.0f);
     for (int o = 0; o < O; ++o) bias[o] = scale ? b[o] * (*scale)[o] + (*shift)[o] : b[o];
@@ -870,7 +961,7 @@ extern "C" {
 int kb_net_create(kb_net** out, int filters, int residuals) {
     KB_REQUIRE_INIT();
     KB_ARG(out, "out");
-    KB_ARG(filters == 64 || filters == 128 || filters == 256, "filters must be 64, 128 or 256");
+    KB_ARG(filters == 64 || filters == 128 || filters == 192 || filters == 256, "filters must be a multiple of 64 up to 256");
     KB_ARG(residuals >= 0 && residuals <= 64, "residuals in [0, 64]");
     kb_net* n = new (std::nothrow) kb_net();
     if (!n) return KB_ERR_ARG;
@@ -890,7 +981,7 @@ int kb_net_destroy(kb_net* n) {
     cudaFree(n->wv); cudaFree(n->fct); cudaFree(n->fcb);
     cudaFree(n->P); cudaFree(n->X); cudaFree(n->Y); cudaFree(n->H);
     cudaFree(n->nan_flag); cudaFree(n->obs_dev); cudaFree(n->pol_dev); cudaFree(n->val_dev);
-    cudaFree(n->fused_w); cudaFree(n->fused_bias);
+    cudaFree(n->fused_w); cudaFree(n->fused_bias); cudaFree(n->ts_dev);
     delete n;
     return KB_OK;
 }
@@ -921,12 +1012,12 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
     BlobCursor c{blob, n_floats};
     std::vector<float> sc, sh;
     const int ntile = F == 64 ? 64 : 128;
-    auto conv_bn = [&](int O, int Cin, int k, int cin_chunks, int slice, int n_tile, int n_total, int relu, bool has_bn) -> int {
+    auto conv_bn = [&](int O, int Cin, int k, int slabs_in, int ksteps, int n_tile, int n_total, int relu, bool has_bn) -> int {
         const float* w = c.take((size_t)O * Cin * k * k);
         const float* b = c.take(O);
         Layer L;
-        L.cin_chunks = cin_chunks;
-        L.slice = slice;
+        L.slabs_in = slabs_in;
+        L.ksteps = ksteps;
         L.n_tile = n_tile;
         L.n_total = n_total;
         L.n_valid = O;
@@ -944,13 +1035,14 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         return KB_OK;
     };
     int r;
-    if ((r = conv_bn(F, 30, 3, IN_CHUNKS, 4, ntile, F, 1, true))) return r;              // conv1 + batchnorm1 + relu
+    const int fs = F / 64;
+    if ((r = conv_bn(F, 30, 3, 1, 2, ntile, F, 1, true))) return r;                   // conv1 + batchnorm1 + relu (32 of 64 input channels)
     for (int i = 0; i < R; ++i) {
-        if ((r = conv_bn(F, F, 3, F / 8, 8, ntile, F, 1, true))) return r;              // residual conv1 + bn1 + relu
-        if ((r = conv_bn(F, F, 3, F / 8, 8, ntile, F, 1, true))) return r;              // residual conv2 + bn2 + relu (+ skip)
+        if ((r = conv_bn(F, F, 3, fs, 4, ntile, F, 1, true))) return r;               // residual conv1 + bn1 + relu
+        if ((r = conv_bn(F, F, 3, fs, 4, ntile, F, 1, true))) return r;               // residual conv2 + bn2 + relu (+ skip)
     }
-    if ((r = conv_bn(128, F, 1, F / 8, 8, 128, 128, 1, true))) return r;                  // policyconv + pbatchnorm + relu
-    if ((r = conv_bn(73, 128, 1, 16, 8, 80, 80, 0, false))) return r;                     // policyconv2 (logits)
+    if ((r = conv_bn(128, F, 1, fs, 4, ntile, 128, 1, true))) return r;               // policyconv + pbatchnorm + relu
+    if ((r = conv_bn(73, 128, 1, 2, 4, 80, 80, 0, false))) return r;                  // policyconv2 (logits)
     {   // value head
         const float* w = c.take(F);
         const float* b = c.take(1);
@@ -983,20 +1075,22 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         std::vector<float> allb;
         FusedParams& fp = net->fp;
         memset(&fp, 0, sizeof(fp));
-        const int XOFF = 0, YOFF = 8 * PLANE_BYTES;
+        const int XOFF = 0, YOFF = SLAB_BYTES;
         fp.n_layers = (int)net->layers.size();
         fp.tower_layers = 1 + 2 * R;
         for (int l = 0; l < fp.n_layers; ++l) {
             const Layer& L = net->layers[l];
             FusedLayer& f = fp.layer[l];
-            f.chunks_in = L.cin_chunks;
+            f.slabs_in = L.slabs_in;
+            f.ksteps = L.ksteps;
             f.n = L.n_total;
+            f.n_sub = L.n_tile;
             f.ntaps = L.ntaps;
             f.relu = L.relu;
             f.skip = 0;
             f.kind = 0;
             f.bias_off = (int)allb.size();
-            f.idesc = ptx::idesc_bf16(128, L.n_total);
+            f.idesc = ptx::idesc_bf16(128, L.n_tile);
             if (l == 0) {                       // conv1: P (parked in Y) -> X
                 f.src_off = YOFF;
                 f.dst_off = XOFF;
@@ -1035,7 +1129,7 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
     return KB_OK;
 }
 
-size_t kb_net_planes_bytes(int batch) { return act_bytes(batch, IN_CHUNKS); }
+size_t kb_net_planes_bytes(int batch) { return act_bytes(batch, IN_SLABS); }
 
 int kb_net_forward_dev(kb_net* net, const void* planes_dev, int batch, float* policy_dev, float* value256_dev) {
     KB_REQUIRE_INIT();
@@ -1093,21 +1187,47 @@ int kb_net_debug_activation(kb_net* net, int which, int board, float* out, int* 
     KB_REQUIRE_INIT();
     KB_ARG(net && out && channels && board >= 0 && board < net->cap_boards, "net/out/board");
     const uint4* buf = which == 0 ? net->P : which == 1 ? net->X : which == 2 ? net->Y : net->H;
-    const int chunks = which == 0 ? IN_CHUNKS : which == 3 ? 16 : net->filters / 8;
+    const int slabs = which == 0 ? IN_SLABS : which == 3 ? 2 : (net->filters + 63) / 64;
+    const int chunks = slabs * 8;
     KB_CUDA(cudaStreamSynchronize(main_stream()));
     const int item = board / NB, slot = board % NB;
-    std::vector<uint16_t> plane((size_t)PLANE_PIX * 8);
-    for (int c = 0; c < chunks; ++c) {
-        KB_CUDA(cudaMemcpy(plane.data(), buf + ((size_t)item * chunks + c) * PLANE_PIX, PLANE_BYTES, cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> slab((size_t)SLAB_BYTES / 2);
+    for (int sl = 0; sl < slabs; ++sl) {
+        KB_CUDA(cudaMemcpy(slab.data(), buf + ((size_t)item * slabs + sl) * SLAB_U4, SLAB_BYTES, cudaMemcpyDeviceToHost));
         for (int q = 0; q < 64; ++q)
-            for (int e = 0; e < 8; ++e) {
-                uint32_t u = (uint32_t)plane[(size_t)tall_pixel(slot, q) * 8 + e] << 16;
+            for (int c = 0; c < 64; ++c) {
+                const int px = tall_pixel(slot, q);
+                uint32_t u = (uint32_t)slab[(size_t)chunk_u4(px, c >> 3) * 8 + (c & 7)] << 16;
                 float f;
                 memcpy(&f, &u, 4);
-                out[(size_t)(c * 8 + e) * 64 + q] = f;
+                out[(size_t)(sl * 64 + c) * 64 + q] = f;
             }
     }
     *channels = chunks * 8;
+    return KB_OK;
+}
+
+// Profiling hook: clock64 stamps of CTA 0's first epilogue thread in k_tower64 (start, region
+// cleared, then per layer [accumulators ready, layer written], softmax start, end).
+int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, int* count) {
+    KB_REQUIRE_INIT();
+    KB_ARG(net, "net");
+    if (enable && !net->ts_dev) {
+        KB_CUDA(cudaMalloc(&net->ts_dev, 64 * sizeof(long long)));
+        KB_CUDA(cudaMemset(net->ts_dev, 0, 64 * sizeof(long long)));
+    }
+    if (out && net->ts_dev) {
+        long long h[64];
+        KB_CUDA(cudaStreamSynchronize(main_stream()));
+        KB_CUDA(cudaMemcpy(h, net->ts_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        int n = 0;
+        while (n < 60 && n < cap && h[n]) { out[n] = h[n]; ++n; }
+        if (count) *count = n;
+    }
+    if (!enable && net->ts_dev) {
+        cudaFree(net->ts_dev);
+        net->ts_dev = nullptr;
+    }
     return KB_OK;
 }
 

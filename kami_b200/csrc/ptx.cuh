@@ -89,6 +89,19 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
            (1ULL << 46);  // descriptor version 1 (sm_100); layout type 0 = SWIZZLE_NONE; base offset 0
 }
+// K-major SWIZZLE_128B descriptor: rows are 128-byte lines (64 bf16), an 8-row group is sbo bytes
+// from the next one; the leading-dimension field is unused for swizzled K-major layouts (set to
+// 1 like CUTLASS), base offset 0: the hardware swizzles the absolute shared-memory address, so a
+// start address that is only 128-byte aligned (a tap shift) is fine (verified on B200).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ULL << 46) |
+           (2ULL << 61);
+}
+// The same descriptor split in words so an issue loop can advance the start address with one add:
+// lo = start address (>>4) | LBO field, hi = SBO | version | layout type.
+__device__ __forceinline__ uint32_t sw128_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint32_t sw128_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

@@ -95,11 +95,12 @@ __device__ void warp_encode_f32(const Pos& p, float* dst) {
         dst[e] = plane_value(p, q, f);
     }
 }
-// bf16 planes in the tall-image layout the conv tower consumes (layout.cuh): channels padded to 32.
+// bf16 planes in the swizzled tall-image layout the conv tower consumes (layout.cuh): the 30
+// features fill channels 0..29 of the input slab (chunks 0..3 of each pixel line).
 __device__ void warp_encode_tall(const Pos& p, int board, uint4* planes) {
     const int lane = lane_id();
     const int item = board / NB, slot = board - item * NB;
-    uint4* base = planes + (size_t)item * IN_CHUNKS * PLANE_PIX;
+    uint4* base = planes + (size_t)item * IN_SLABS * SLAB_U4;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int q = lane + 32 * h;
@@ -108,7 +109,7 @@ __device__ void warp_encode_tall(const Pos& p, int board, uint4* planes) {
         const int t = type_at(p, sq);
         const int hot = t < 0 ? -1 : 18 + (color_at(p, sq) != p.ctm ? 6 : 0) + t;
 #pragma unroll
-        for (int c = 0; c < IN_CHUNKS; ++c) {
+        for (int c = 0; c < 4; ++c) {
             u32 w[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -118,7 +119,7 @@ __device__ void warp_encode_tall(const Pos& p, int board, uint4* planes) {
                 const __nv_bfloat162 b = __floats2bfloat162_rn(v0, v1);
                 w[k] = *reinterpret_cast<const u32*>(&b);
             }
-            base[c * PLANE_PIX + px] = make_uint4(w[0], w[1], w[2], w[3]);
+            base[chunk_u4(px, c)] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
@@ -719,20 +720,20 @@ __global__ void __launch_bounds__(128) k_encode_tall(const Pos* pos, int n, uint
     const Pos p = pos[b];
     warp_encode_tall(p, b, planes);
 }
-// fp32 [n][64][30] observations (NN::infer's input) -> bf16 tall-image planes
+// fp32 [n][64][30] observations (NN::infer's input) -> bf16 swizzled tall-image input slab
 __global__ void __launch_bounds__(128) k_obs_to_tall(const float* obs, int n, uint4* planes) {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= n) return;
     const int lane = lane_id();
     const int item = b / NB, slot = b - item * NB;
-    uint4* base = planes + (size_t)item * IN_CHUNKS * PLANE_PIX;
+    uint4* base = planes + (size_t)item * IN_SLABS * SLAB_U4;
     const float* src = obs + (size_t)b * 64 * NFEATURES;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int q = lane + 32 * h;
         const int px = tall_pixel(slot, q);
 #pragma unroll
-        for (int c = 0; c < IN_CHUNKS; ++c) {
+        for (int c = 0; c < 4; ++c) {
             u32 wv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -742,7 +743,7 @@ __global__ void __launch_bounds__(128) k_obs_to_tall(const float* obs, int n, ui
                 const __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
                 wv[k] = *reinterpret_cast<const u32*>(&bb);
             }
-            base[c * PLANE_PIX + px] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            base[chunk_u4(px, c)] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
     }
 }
