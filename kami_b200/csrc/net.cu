@@ -38,6 +38,8 @@ struct ConvParams {
     int n_valid;  // real output channels
     int ntaps;    // 9 (3x3, pad 1) or 1 (1x1)
     int relu;
+    long long* ts;  // optional profiling hook: wait-cycle counters of CTA 0's MMA thread
+    int skew;       // k_conv2: weight blocks issued tile-major at each end of a pass (0..3)
 };
 
 template <int N_TILE>
@@ -45,12 +47,13 @@ struct ConvCfg {
     static constexpr int MT = 4;                       // 4 M tiles x 16 tall rows = the 64 rows of an item
     static constexpr int A_BYTES = SLAB_BYTES;         // one 64-channel slab of an item
     static constexpr int B_BYTES = N_TILE * LINE_BYTES;  // [n][64 k] swizzled weight block
-    static constexpr int NSTAGE = 4;
+    static constexpr int NSTAGE = N_TILE > 80 ? 3 : 4;
     static constexpr int ACC_COLS = MT * N_TILE;
     static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
-    static constexpr int BAR_BYTES = 1024;
+    static constexpr int BAR_BYTES = 2048;             // mbarriers, TMEM slot, folded biases (<= 256 floats at +1024)
     static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;  // stages stay 1024-byte aligned
-    static constexpr int SMEM = BAR_BYTES + 2 * A_BYTES + NSTAGE * B_STRIDE;
+    static constexpr int STG_BYTES = 4 * 4096;         // epilogue staging: one 32-pixel x 128-byte tile per warp
+    static constexpr int SMEM = BAR_BYTES + 2 * A_BYTES + NSTAGE * B_STRIDE + STG_BYTES;
     static_assert(ACC_COLS <= 512, "accumulators must fit TMEM");
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(N_TILE % 16 == 0 && N_TILE <= 256, "UMMA N for M=128");
@@ -59,6 +62,15 @@ struct ConvCfg {
 // byte offset of tap (dy,dx) for M tile mt inside a slab: first pixel of the tile's first row group
 __device__ __forceinline__ int tap_offset(int mt, int dy, int dx) { return ((16 * mt + dy) * TALL_PITCH + 1 + dx) * LINE_BYTES; }
 
+// Warp roles: warp 0 weight (B) producer, warp 1 tcgen05.mma issuer, warp 2 TMEM allocator,
+// warp 3 activation (A) producer, warps 4-7 epilogue (one per TMEM lane quarter).
+//
+// Epilogue data path (bf16 output): a warp owns 32 rows of an M tile = 4 tall rows x 8 pixels.
+// For each 64-channel half of the accumulator it builds the 4 row segments (8 pixels x 128 B =
+// 1024 contiguous bytes of the output slab, already swizzled) in a 4 KB staging tile and hands
+// them to the TMA as bulk shared->global stores; the residual skip input arrives the same way
+// (bulk global->shared into the staging tile, added in fp32).  No scattered 16-byte global
+// accesses: every global transaction of the kernel is a >= 1 KB bulk copy.
 template <int N_TILE>
 __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     using C = ConvCfg<N_TILE>;
@@ -71,9 +83,12 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     auto a_empty = [&](int s) { return bar0 + 8u * (10 + s); };
     auto t_full = [&](int s) { return bar0 + 8u * (12 + s); };
     auto t_empty = [&](int s) { return bar0 + 8u * (14 + s); };
+    auto skip_full = [&](int q) { return bar0 + 8u * (16 + q); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    float* sbias = reinterpret_cast<float*>(smem + 1024);
     const uint32_t a_smem = bar0 + C::BAR_BYTES;
     const uint32_t b_smem = a_smem + 2 * C::A_BYTES;
+    constexpr int STG_OFF = C::BAR_BYTES + 2 * C::A_BYTES + C::NSTAGE * C::B_STRIDE;
 
     const int kslices = P.slabs_in;
     const int npass = P.n_total / N_TILE;
@@ -85,6 +100,7 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
         for (int s = 0; s < 4; ++s) {
             ptx::mbar_init(b_full(s), 1);
             ptx::mbar_init(b_empty(s), 1);
+            ptx::mbar_init(skip_full(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(a_full(s), 1);
@@ -98,14 +114,15 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
         ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
         ptx::tmem_relinquish();
     }
+    for (int i = threadIdx.x; i < P.n_total && i < 256; i += blockDim.x) sbias[i] = P.bias[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ===== producer: bulk TMA copies of activation slabs (A) and weight blocks (B) =====
-        auto issue_a = [&](int job) {
+    if (warp == 3 && lane == 0) {
+        // ===== A producer: one bulk copy per (item, pass, slab) job, double buffered =====
+        for (int job = 0; job < total_jobs; ++job) {
             const int ii = job / jobs_per_item, rem = job - ii * jobs_per_item;
             const int ks = rem % kslices;
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
@@ -114,17 +131,17 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
             ptx::mbar_arrive_expect_tx(a_full(buf), C::A_BYTES);
             const uint4* src = P.in + ((size_t)item * P.slabs_in + ks) * SLAB_U4;
             ptx::bulk_g2s(a_smem + buf * C::A_BYTES, src, C::A_BYTES, a_full(buf));
-        };
-        if (total_jobs > 0) issue_a(0);
+        }
+    } else if (warp == 0 && lane == 0) {
+        // ===== B producer: weight blocks in consumption order through the stage ring =====
         int stage = 0, sphase = 0;
         for (int job = 0; job < total_jobs; ++job) {
-            if (job + 1 < total_jobs) issue_a(job + 1);
             const int rem = job % jobs_per_item;
             const int pass = rem / kslices, ks = rem - pass * kslices;
-            for (int tap = 0; tap < P.ntaps; ++tap) {
+            const uint4* src = P.w + (size_t)(pass * kslices + ks) * P.ntaps * (C::B_BYTES / 16);
+            for (int tap = 0; tap < P.ntaps; ++tap, src += C::B_BYTES / 16) {
                 ptx::mbar_wait(b_empty(stage), sphase ^ 1);
                 ptx::mbar_arrive_expect_tx(b_full(stage), C::B_BYTES);
-                const uint4* src = P.w + ((size_t)(pass * kslices + ks) * P.ntaps + tap) * (C::B_BYTES / 16);
                 ptx::bulk_g2s(b_smem + stage * C::B_STRIDE, src, C::B_BYTES, b_full(stage));
                 if (++stage == C::NSTAGE) {
                     stage = 0;
@@ -136,16 +153,22 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
         // ===== MMA issuer: one thread drives the tensor core =====
         constexpr uint32_t idesc = ptx::idesc_bf16(128, N_TILE);
         int stage = 0, sphase = 0, acc_count = 0;
+        const bool prof = P.ts && blockIdx.x == 0;
+        long long w_t = 0, w_a = 0, w_b = 0, t_begin = prof ? clock64() : 0, c0 = 0;
         for (int job = 0; job < total_jobs; ++job) {
             const int rem = job % jobs_per_item;
             const int ks = rem % kslices;
             const int buf = job & 1;
             const int acc = acc_count % C::NACC;
             if (ks == 0) {
+                if (prof) c0 = clock64();
                 ptx::mbar_wait(t_empty(acc), ((acc_count / C::NACC) & 1) ^ 1);
                 ptx::tc_fence_after();
+                if (prof) w_t += clock64() - c0;
             }
+            if (prof) c0 = clock64();
             ptx::mbar_wait(a_full(buf), (job >> 1) & 1);
+            if (prof) w_a += clock64() - c0;
             // descriptor words: start addresses advance by plain adds (16-byte units)
             const uint32_t a_lo0 = ptx::sw128_lo(a_smem + buf * C::A_BYTES);
             const uint32_t a_hi = ptx::sw128_hi(TALL_PITCH * LINE_BYTES), b_hi = ptx::sw128_hi(1024);
@@ -154,8 +177,10 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
             for (int tap = 0; tap < P.ntaps; ++tap) {
                 const int dy = P.ntaps == 9 ? tap / 3 - 1 : 0, dx = P.ntaps == 9 ? tap % 3 - 1 : 0;
                 const uint32_t a_tap = a_lo0 + (uint32_t)((dy * TALL_PITCH + dx + 1) * (LINE_BYTES / 16));
+                if (prof) c0 = clock64();
                 ptx::mbar_wait(b_full(stage), sphase);
                 ptx::tc_fence_after();
+                if (prof) w_b += clock64() - c0;
                 const uint32_t b_lo0 = ptx::sw128_lo(b_smem + stage * C::B_STRIDE);
                 uint32_t first = (ks | tap) == 0 ? 0u : 1u;
                 for (int kk = 0; kk < ksteps; ++kk) {
@@ -179,16 +204,31 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
                 ++acc_count;
             }
         }
+        if (prof) {
+            P.ts[0] = clock64() - t_begin;
+            P.ts[1] = w_t;
+            P.ts[2] = w_a;
+            P.ts[3] = w_b;
+        }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> bias/ReLU/skip -> bf16 (or fp32 logits) -> global =====
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         int acc_count = 0;
+        uint8_t* stg = smem + STG_OFF + q * 4096;
+        const uint32_t stg_s = ptx::smem_u32(stg);
+        uint32_t skip_phase = 0;
+        bool store_pending = false;
+        const bool eprof = P.ts && blockIdx.x == 0 && q == 0;
+        long long e_full = 0, e_store = 0, e_tmem = 0, e_skip = 0, e_math = 0, e_issue = 0, ec = 0;
+#define KB_EP(var) do { if (eprof) { const long long now_ = clock64(); var += now_ - ec; ec = now_; } } while (0)
+        if (eprof) ec = clock64();
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             for (int pass = 0; pass < npass; ++pass, ++acc_count) {
                 const int acc = acc_count % C::NACC;
                 ptx::mbar_wait(t_full(acc), (acc_count / C::NACC) & 1);
                 ptx::tc_fence_after();
+                KB_EP(e_full);
 #pragma unroll 1
                 for (int mt = 0; mt < C::MT; ++mt) {
                     const int r = 32 * q + lane;          // row of the M tile == TMEM lane
@@ -199,68 +239,477 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
                     const int px = R * TALL_PITCH + 1 + x;
                     const int board = item * NB + slot;
                     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * C::ACC_COLS + mt * N_TILE;
+                    if (P.out_f32) {
 #pragma unroll 1
-                    for (int cg2 = 0; cg2 < N_TILE / 16; cg2 += 2) {
-                        // two column groups (32 fp32 columns) per round trip to TMEM
-                        uint32_t v[2][16];
-                        ptx::tmem_ld16(taddr + cg2 * 16, v[0]);
-                        if (cg2 + 1 < N_TILE / 16) ptx::tmem_ld16(taddr + (cg2 + 1) * 16, v[1]);
-                        ptx::tmem_ld_wait();
-                        if (!valid) continue;
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int cg = cg2 + g;
-                            if (cg >= N_TILE / 16) break;
+                        for (int cg = 0; cg < N_TILE / 16; ++cg) {
+                            uint32_t v[16];
+                            ptx::tmem_ld16(taddr + cg * 16, v);
+                            ptx::tmem_ld_wait();
+                            if (!valid || board >= P.boards) continue;
                             const int ch0 = pass * N_TILE + cg * 16;
-                            float f[16];
+                            float* dst = P.out_f32 + ((size_t)board * 64 + (y * 8 + x)) * P.n_valid;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                f[j] = __uint_as_float(v[g][j]) + __ldg(P.bias + ch0 + j);
-                                if (P.relu) f[j] = fmaxf(f[j], 0.0f);
+                                float f = __uint_as_float(v[j]) + sbias[ch0 + j];
+                                if (P.relu) f = fmaxf(f, 0.0f);
+                                if (ch0 + j < P.n_valid) dst[ch0 + j] = f;
                             }
-                            if (P.out_f32) {
-                                if (board < P.boards) {
-                                    float* dst = P.out_f32 + ((size_t)board * 64 + (y * 8 + x)) * P.n_valid;
+                        }
+                        continue;
+                    }
+                    if constexpr (N_TILE % 64 == 0) {
+                        // row segments of this warp: tall rows 16*mt + 4*q + g, g = 0..3 (lanes 8g..8g+7)
+                        const int R0 = 16 * mt + 4 * q;
+                        auto seg_valid = [&](int g) { const int Rg = R0 + g; return Rg >= 1 && (Rg - 1) % 9 < 8; };
+#pragma unroll 1
+                        for (int half = 0; half < N_TILE / 64; ++half) {
+                            const int ch0 = pass * N_TILE + half * 64;
+                            const size_t slab_u4 = ((size_t)item * P.slabs_out + (ch0 >> 6)) * SLAB_U4;
+                            if (store_pending) {  // the previous tile's bulk stores must have read the staging tile
+                                if (lane == 0) ptx::bulk_wait_read0();
+                                __syncwarp();
+                                store_pending = false;
+                            }
+                            KB_EP(e_store);
+                            if (P.skip && lane == 0) {
+                                int nv = 0;
+                                for (int g = 0; g < 4; ++g) nv += seg_valid(g) ? 1 : 0;
+                                ptx::mbar_arrive_expect_tx(skip_full(q), 1024u * nv);
+                                for (int g = 0; g < 4; ++g)
+                                    if (seg_valid(g))
+                                        ptx::bulk_g2s(stg_s + g * 1024, P.skip + slab_u4 + (size_t)((R0 + g) * TALL_PITCH + 1) * 8, 1024, skip_full(q));
+                            }
+                            uint32_t v[4][16];
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j)
-                                        if (ch0 + j < P.n_valid) dst[ch0 + j] = f[j];
-                                }
-                            } else {
+                            for (int g = 0; g < 4; ++g) ptx::tmem_ld16(taddr + half * 64 + g * 16, v[g]);
+                            ptx::tmem_ld_wait();
+                            if (mt == C::MT - 1 && half == N_TILE / 64 - 1) {  // accumulator drained: release it early
+                                ptx::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive(t_empty(acc));
+                            }
+                            KB_EP(e_tmem);
+                            if (P.skip) {
+                                ptx::mbar_wait(skip_full(q), skip_phase);
+                                skip_phase ^= 1;
+                            }
+                            KB_EP(e_skip);
+                            if (valid) {
+                                uint4* line = reinterpret_cast<uint4*>(stg + lane * 128);
 #pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    const int ch = ch0 + 8 * h;  // first of 8 channels
-                                    const size_t idx = ((size_t)item * P.slabs_out + (ch >> 6)) * SLAB_U4 + chunk_u4(px, (ch >> 3) & 7);
+                                for (int j = 0; j < 8; ++j) {  // 8 channels = one 16-byte chunk
+                                    float f[8];
+                                    const float4 b0 = *reinterpret_cast<const float4*>(sbias + ch0 + 8 * j);
+                                    const float4 b1 = *reinterpret_cast<const float4*>(sbias + ch0 + 8 * j + 4);
+                                    const uint32_t* vv = &v[j >> 1][(j & 1) * 8];
+                                    f[0] = __uint_as_float(vv[0]) + b0.x; f[1] = __uint_as_float(vv[1]) + b0.y;
+                                    f[2] = __uint_as_float(vv[2]) + b0.z; f[3] = __uint_as_float(vv[3]) + b0.w;
+                                    f[4] = __uint_as_float(vv[4]) + b1.x; f[5] = __uint_as_float(vv[5]) + b1.y;
+                                    f[6] = __uint_as_float(vv[6]) + b1.z; f[7] = __uint_as_float(vv[7]) + b1.w;
+                                    if (P.relu) {
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+                                    }
+                                    uint4* cp = line + (j ^ (px & 7));
                                     if (P.skip) {
-                                        const uint4 s4 = P.skip[idx];
+                                        const uint4 s4 = *cp;
                                         const __nv_bfloat162* sb = reinterpret_cast<const __nv_bfloat162*>(&s4);
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) {
                                             const float2 sv = __bfloat1622float2(sb[k]);
-                                            f[h * 8 + 2 * k] += sv.x;
-                                            f[h * 8 + 2 * k + 1] += sv.y;
+                                            f[2 * k] += sv.x;
+                                            f[2 * k + 1] += sv.y;
                                         }
                                     }
                                     uint32_t w4[4];
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
-                                        const __nv_bfloat162 b = __floats2bfloat162_rn(f[h * 8 + 2 * k], f[h * 8 + 2 * k + 1]);
+                                        const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
                                         w4[k] = *reinterpret_cast<const uint32_t*>(&b);
                                     }
-                                    P.out[idx] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                                    *cp = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                                 }
+                                ptx::fence_proxy_async_smem();
                             }
+                            __syncwarp();
+                            KB_EP(e_math);
+                            if (lane == 0) {
+                                for (int g = 0; g < 4; ++g)
+                                    if (seg_valid(g))
+                                        ptx::bulk_s2g(P.out + slab_u4 + (size_t)((R0 + g) * TALL_PITCH + 1) * 8, stg_s + g * 1024, 1024);
+                                ptx::bulk_commit();
+                            }
+                            store_pending = true;
+                            KB_EP(e_issue);
                         }
                     }
                 }
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(t_empty(acc));
+                if (P.out_f32 || N_TILE % 64 != 0) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(t_empty(acc));
+                }
             }
         }
+        if (lane == 0) ptx::bulk_wait0();  // shared memory must outlive the last bulk stores
+        if (eprof && lane == 0) {
+            P.ts[4] = e_full; P.ts[5] = e_store; P.ts[6] = e_tmem; P.ts[7] = e_skip; P.ts[8] = e_math; P.ts[9] = e_issue;
+        }
+#undef KB_EP
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_conv2: the same implicit-GEMM convolution on CTA PAIRS (cluster of 2, tcgen05 cta_group::2).
+// Each CTA of a pair owns one item (its A slabs and its 128-lane accumulators); the even CTA
+// issues M = 256 MMAs that read A from both CTAs and HALF of every weight block from each CTA,
+// so an SM streams and re-reads only N_TILE/2 weight rows per tap.  The 128x128x16 single-CTA
+// MMA needs 128 B/clk of shared-memory operand reads (the whole port); the paired form needs 96
+// and halves the L2->SM weight traffic.  Eight epilogue warps (two per TMEM lane quarter).
+//
+// Barrier protocol: full barriers live in the even (leader) CTA with two arrivals -- its own
+// arrive.expect_tx and a forwarded arrive from the odd CTA (warp 1 of the odd CTA waits for the
+// local TMA completion and arrives remotely); empty / accumulator-full barriers are signalled in
+// both CTAs by multicast tcgen05.commit; accumulator-empty collects all 16 epilogue warps.
+// ------------------------------------------------------------------------------------------
+template <int N_TILE>
+struct Conv2Cfg {
+    static constexpr int MT = 4;
+    static constexpr int HALVES = N_TILE / 64;
+    static constexpr int A_BYTES = SLAB_BYTES;
+    static constexpr int B_HALF = N_TILE * LINE_BYTES / 2;  // this CTA's rows of a [n][64 k] weight block
+    static constexpr int NSTAGE = 4;
+    static constexpr int ACC_COLS = MT * N_TILE;
+    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int BAR_BYTES = 2048;
+    static constexpr int B_STRIDE = (B_HALF + 1023) / 1024 * 1024;
+    static constexpr int STG_BYTES = 8 * 4096;
+    static constexpr int SMEM = BAR_BYTES + 2 * A_BYTES + NSTAGE * B_STRIDE + STG_BYTES;
+    static_assert(N_TILE == 128 && ACC_COLS == 512, "one pass fills TMEM; two channel halves per tile");
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int N_TILE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_conv2(const ConvParams P) {
+    using C = Conv2Cfg<N_TILE>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = ptx::uniform_warp_id(), lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const uint32_t bar0 = ptx::smem_u32(smem);
+    auto b_full = [&](int s) { return bar0 + 8u * s; };
+    auto b_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto a_full = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto a_empty = [&](int s) { return bar0 + 8u * (10 + s); };
+    auto t_full = [&](int mt) { return bar0 + 8u * (12 + mt); };   // accumulator of M tile mt complete (both CTAs)
+    auto t_empty = [&](int mt) { return bar0 + 8u * (16 + mt); };  // ... drained by all 16 epilogue warps of the pair
+    auto skip_full = [&](int e) { return bar0 + 8u * (20 + e); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    float* sbias = reinterpret_cast<float*>(smem + 1024);
+    const uint32_t a_smem = bar0 + C::BAR_BYTES;
+    const uint32_t b_smem = a_smem + 2 * C::A_BYTES;
+    constexpr int STG_OFF = C::BAR_BYTES + 2 * C::A_BYTES + C::NSTAGE * C::B_STRIDE;
+
+    const int kslices = P.slabs_in;
+    const int npass = P.n_total / N_TILE;
+    const int pair0 = (int)blockIdx.x >> 1, pair_stride = (int)gridDim.x >> 1;
+    const int total_pairs = (P.items + 1) >> 1;
+    const int my_pairs = total_pairs > pair0 ? (total_pairs - 1 - pair0) / pair_stride + 1 : 0;
+    const int jobs_per_item = npass * kslices;
+    const int total_jobs = my_pairs * jobs_per_item;
+
+    if (threadIdx.x == 0) {
+        const uint32_t full_count = rank == 0 ? 2u : 1u;
+        for (int s = 0; s < 4; ++s) {
+            ptx::mbar_init(b_full(s), full_count);
+            ptx::mbar_init(b_empty(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(a_full(s), full_count);
+            ptx::mbar_init(a_empty(s), 1);
+        }
+        for (int mt = 0; mt < C::MT; ++mt) {
+            ptx::mbar_init(t_full(mt), 1);
+            ptx::mbar_init(t_empty(mt), 16);
+        }
+        for (int e = 0; e < 8; ++e) ptx::mbar_init(skip_full(e), 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512);
+        ptx::tmem_relinquish2();
+    }
+    for (int i = threadIdx.x; i < P.n_total && i < 256; i += blockDim.x) sbias[i] = P.bias[i];
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 3) {
+        // ===== A producer: this CTA's item, one bulk copy per (pair, pass, slab) job =====
+        for (int job = 0; job < total_jobs; ++job) {
+            const int ii = job / jobs_per_item, rem = job - ii * jobs_per_item;
+            const int ks = rem % kslices;
+            int item = 2 * (pair0 + ii * pair_stride) + (int)rank;
+            if (item >= P.items) item = P.items - 1;  // odd item count: the last pair's odd CTA recomputes a live item, writes nothing
+            const int buf = job & 1;
+            ptx::mbar_wait(a_empty(buf), ((job >> 1) & 1) ^ 1);
+            const uint4* src = P.in + ((size_t)item * P.slabs_in + ks) * SLAB_U4;
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(a_full(buf), C::A_BYTES);
+                ptx::bulk_g2s(a_smem + buf * C::A_BYTES, src, C::A_BYTES, a_full(buf));
+            }
+            __syncwarp();
+        }
+    } else if (warp == 0) {
+        // ===== B producer: this CTA's half (N_TILE/2 rows) of every weight block =====
+        int stage = 0, sphase = 0;
+        for (int job = 0; job < total_jobs; ++job) {
+            const int rem = job % jobs_per_item;
+            const int pass = rem / kslices, ks = rem - pass * kslices;
+            const uint4* src = P.w + (size_t)(pass * kslices + ks) * P.ntaps * (N_TILE * LINE_BYTES / 16) + rank * (C::B_HALF / 16);
+            for (int tap = 0; tap < P.ntaps; ++tap, src += N_TILE * LINE_BYTES / 16) {
+                ptx::mbar_wait(b_empty(stage), sphase ^ 1);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(b_full(stage), C::B_HALF);
+                    ptx::bulk_g2s(b_smem + stage * C::B_STRIDE, src, C::B_HALF, b_full(stage));
+                }
+                __syncwarp();
+                if (++stage == C::NSTAGE) {
+                    stage = 0;
+                    sphase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 1) {
+        // ===== odd CTA: forward local TMA completions to the leader's full barriers =====
+        int stage = 0, sphase = 0;
+        for (int job = 0; job < total_jobs; ++job) {
+            const int buf = job & 1;
+            ptx::mbar_wait(a_full(buf), (job >> 1) & 1);
+            if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(a_full(buf), 0));
+            __syncwarp();
+            for (int tap = 0; tap < P.ntaps; ++tap) {
+                ptx::mbar_wait(b_full(stage), sphase);
+                if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(b_full(stage), 0));
+                __syncwarp();
+                if (++stage == C::NSTAGE) {
+                    stage = 0;
+                    sphase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== leader MMA issuer: one elected thread drives both SMs' tensor cores =====
+        // A pass is U = slabs x taps weight blocks of 4 k-steps for each of the 4 M tiles.  TMEM holds
+        // exactly one pass (4 x 128 columns), so the accumulators are handed over tile by tile: the
+        // first and the last SKEW blocks of a pass are issued tile-major (all blocks for tile 0, then
+        // tile 1, ...), the middle block-major.  Tile mt then completes 3*(3-mt) block-times before the
+        // pass ends and is first needed 3*mt block-times after the next pass starts, which is the
+        // window the epilogue warps drain it in.
+        constexpr uint32_t idesc = ptx::idesc_bf16(256, N_TILE);
+        constexpr int SKEW = 3;  // <= NSTAGE - 1 weight stages stay resident during a tile-major group
+        const int ntaps = P.ntaps, ksteps = P.ksteps;
+        const int U = kslices * ntaps;
+        const int G = U / 2 < P.skew ? U / 2 : (P.skew < SKEW ? P.skew : SKEW);
+        const int total_passes = my_pairs * npass;
+        const uint32_t a_hi = ptx::sw128_hi(TALL_PITCH * LINE_BYTES), b_hi = ptx::sw128_hi(1024);
+        int gb_ready = 0, gj_ready = 0;  // weight blocks / activation slabs already waited for (global counters)
+        const bool prof = P.ts && blockIdx.x == 0;
+        long long w_t = 0, w_a = 0, w_b = 0, t_begin = prof ? clock64() : 0, c0 = 0;
+        uint32_t a_tap = 0, b_lo0 = 0;
+        auto open_block = [&](int pi, int u) {  // wait for block u's operands, set up its descriptor bases
+            const int ks = ntaps == 9 ? u / 9 : u, tap = u - ks * ntaps;
+            const int gj = pi * kslices + ks, gb = pi * U + u;
+            if (gj_ready <= gj) {
+                if (prof) c0 = clock64();
+                for (; gj_ready <= gj; ++gj_ready) ptx::mbar_wait(a_full(gj_ready & 1), (gj_ready >> 1) & 1);
+                if (prof) w_a += clock64() - c0;
+            }
+            if (gb_ready <= gb) {
+                if (prof) c0 = clock64();
+                for (; gb_ready <= gb; ++gb_ready) ptx::mbar_wait(b_full(gb_ready % C::NSTAGE), (gb_ready / C::NSTAGE) & 1);
+                ptx::tc_fence_after();
+                if (prof) w_b += clock64() - c0;
+            }
+            const int dy = ntaps == 9 ? tap / 3 - 1 : 0, dx = ntaps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
+            a_tap = ptx::sw128_lo(a_smem + (gj & 1) * C::A_BYTES) + (uint32_t)((dy * TALL_PITCH + dx + 1) * (LINE_BYTES / 16));
+            b_lo0 = ptx::sw128_lo(b_smem + (gb % C::NSTAGE) * C::B_STRIDE);
+        };
+        constexpr uint32_t MT_STEP = 16 * TALL_PITCH * LINE_BYTES / 16;  // descriptor start-address units between M tiles
+        auto mma_block_all = [&](int pi, int u) {  // block-major: every k-step feeds the four tiles
+            open_block(pi, u);
+            if (ptx::elect_one()) {
+                uint32_t acc = u == 0 ? 0u : 1u;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
+#pragma unroll
+                    for (int mt = 0; mt < C::MT; ++mt)
+                        ptx::mma_bf16_2cta(tmem_base + mt * N_TILE, ptx::desc_pack(a_tap + kk * 2 + mt * MT_STEP, a_hi), bdesc, idesc, acc);
+                    acc = 1u;
+                }
+            }
+            __syncwarp();
+        };
+        auto mma_block_one = [&](int pi, int u, int mt) {  // tile-major: one tile's k-steps of block u
+            open_block(pi, u);
+            const uint32_t d = tmem_base + mt * N_TILE, a0 = a_tap + mt * MT_STEP;
+            if (ptx::elect_one()) {
+                uint32_t acc = u == 0 ? 0u : 1u;
+#pragma unroll 2
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    ptx::mma_bf16_2cta(d, ptx::desc_pack(a0 + kk * 2, a_hi), ptx::desc_pack(b_lo0 + kk * 2, b_hi), idesc, acc);
+                    acc = 1u;
+                }
+            }
+            __syncwarp();
+        };
+        auto release_block = [&](int pi, int u) {  // every tile has consumed block u: free its stage (and slab)
+            const int ks = ntaps == 9 ? u / 9 : u;
+            if (ptx::elect_one()) {
+                ptx::mma_commit_2cta(b_empty((pi * U + u) % C::NSTAGE));
+                if (u + 1 == (ks + 1) * ntaps) ptx::mma_commit_2cta(a_empty((pi * kslices + ks) & 1));
+            }
+            __syncwarp();
+        };
+        for (int pi = 0; pi < total_passes; ++pi) {
+            for (int mt = 0; mt < C::MT; ++mt) {  // head: tile-major, each tile waits for its own drain
+                if (prof) c0 = clock64();
+                ptx::mbar_wait(t_empty(mt), (pi & 1) ^ 1);
+                ptx::tc_fence_after();
+                if (prof) w_t += clock64() - c0;
+                for (int u = 0; u < G; ++u) mma_block_one(pi, u, mt);
+            }
+            for (int u = 0; u < G; ++u) release_block(pi, u);
+            for (int u = G; u < U - G; ++u) {     // middle: block-major
+                mma_block_all(pi, u);
+                release_block(pi, u);
+            }
+            for (int mt = 0; mt < C::MT; ++mt) {  // tail: tile-major, each tile is handed over as it completes
+                for (int u = U - G; u < U; ++u) mma_block_one(pi, u, mt);
+                if (ptx::elect_one()) ptx::mma_commit_2cta(t_full(mt));
+                __syncwarp();
+            }
+            for (int u = U - G; u < U; ++u) release_block(pi, u);
+        }
+        if (prof && lane == 0) {
+            P.ts[0] = clock64() - t_begin;
+            P.ts[1] = w_t;
+            P.ts[2] = w_a;
+            P.ts[3] = w_b;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps; warp (q, h) takes the steps (mt, half) with (mt*HALVES + half) % 2 == h =====
+        const int e = warp - 4, q = warp & 3, h = e >> 2;
+        int acc_count = 0;
+        uint8_t* stg = smem + STG_OFF + e * 4096;
+        const uint32_t stg_s = ptx::smem_u32(stg);
+        uint32_t skip_phase = 0;
+        const bool eprof = P.ts && blockIdx.x == 0 && e == 0;
+        long long e_full = 0, e_store = 0, e_tmem = 0, e_skip = 0, e_math = 0, e_issue = 0, ec = 0;
+#define KB_EP(var) do { if (eprof) { const long long now_ = clock64(); var += now_ - ec; ec = now_; } } while (0)
+        if (eprof) ec = clock64();
+        for (int ii = 0; ii < my_pairs; ++ii) {
+            const int item = 2 * (pair0 + ii * pair_stride) + (int)rank;
+            const bool live = item < P.items;
+            for (int pass = 0; pass < npass; ++pass, ++acc_count) {
+#pragma unroll 1
+                for (int mt = 0; mt < C::MT; ++mt) {  // this warp: channel half h of every M tile
+                    const int half = h;
+                    ptx::mbar_wait(t_full(mt), acc_count & 1);
+                    ptx::tc_fence_after();
+                    KB_EP(e_full);
+                    const int r = 32 * q + lane;          // row of the M tile == TMEM lane
+                    const int R = 16 * mt + (r >> 3);     // tall row
+                    const int x = r & 7;
+                    const bool valid = live && R >= 1 && (R - 1) % 9 < 8;
+                    const int px = R * TALL_PITCH + 1 + x;
+                    // row segment g (lanes 8g..8g+7) = tall row 16*mt + 4*q + g; lane g < 4 moves it
+                    const int Rg = 16 * mt + 4 * q + lane;
+                    const bool mover = lane < 4 && live && Rg >= 1 && (Rg - 1) % 9 < 8;
+                    const int nv = __popc(__ballot_sync(0xffffffffu, mover));
+                    const int ch0 = pass * N_TILE + half * 64;
+                    const size_t seg_u4 = ((size_t)item * P.slabs_out + (ch0 >> 6)) * SLAB_U4 + (size_t)(Rg * TALL_PITCH + 1) * 8;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + mt * N_TILE + half * 64;
+                    if (lane < 4) ptx::bulk_wait_read0();  // the previous step's stores have read the staging tile
+                    __syncwarp();
+                    KB_EP(e_store);
+                    if (P.skip && nv) {
+                        if (lane == 0) ptx::mbar_arrive_expect_tx(skip_full(e), 1024u * nv);
+                        __syncwarp();
+                        if (mover) ptx::bulk_g2s(stg_s + lane * 1024, P.skip + seg_u4, 1024, skip_full(e));
+                    }
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) ptx::tmem_ld16(taddr + g * 16, v[g]);
+                    ptx::tmem_ld_wait();
+                    ptx::tc_fence_before();  // this warp's share of tile mt is in registers: hand it back
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(t_empty(mt), 0));
+                    KB_EP(e_tmem);
+                    if (P.skip && nv) {
+                        ptx::mbar_wait(skip_full(e), skip_phase);
+                        skip_phase ^= 1;
+                    }
+                    KB_EP(e_skip);
+                    if (valid) {
+                        uint4* line = reinterpret_cast<uint4*>(stg + lane * 128);
+                        const int sw = px & 7;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {  // 16 channels = two 16-byte chunks per TMEM column group
+                            float4 bb[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) bb[k] = *reinterpret_cast<const float4*>(sbias + ch0 + 16 * g + 4 * k);
+                            const float* bf = reinterpret_cast<const float*>(bb);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                uint4* cp = line + ((2 * g + c) ^ sw);
+                                uint32_t w4[4];
+                                if (P.skip) {  // x = skip + relu(conv + bias): ReLU before the add, none after (nn.cpp:31)
+                                    const uint4 s4 = *cp;
+                                    const uint32_t sk[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const int i0 = 8 * c + 2 * k;
+                                        const float lo = fmaxf(__uint_as_float(v[g][i0]) + bf[i0], 0.0f) + __uint_as_float(sk[k] << 16);
+                                        const float hi = fmaxf(__uint_as_float(v[g][i0 + 1]) + bf[i0 + 1], 0.0f) + __uint_as_float(sk[k] & 0xffff0000u);
+                                        w4[k] = ptx::pack_bf16x2(lo, hi);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const int i0 = 8 * c + 2 * k;
+                                        w4[k] = ptx::pack_relu_bf16x2(__uint_as_float(v[g][i0]) + bf[i0], __uint_as_float(v[g][i0 + 1]) + bf[i0 + 1]);
+                                    }
+                                }
+                                *cp = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                            }
+                        }
+                        ptx::fence_proxy_async_smem();
+                    }
+                    __syncwarp();
+                    KB_EP(e_math);
+                    if (mover) {
+                        ptx::bulk_s2g(P.out + seg_u4, stg_s + lane * 1024, 1024);
+                        ptx::bulk_commit();
+                    }
+                    KB_EP(e_issue);
+                }
+            }
+        }
+        if (lane < 4) ptx::bulk_wait0();  // shared memory must outlive the last bulk stores
+        if (eprof && lane == 0) {
+            P.ts[4] = e_full; P.ts[5] = e_store; P.ts[6] = e_tmem; P.ts[7] = e_skip; P.ts[8] = e_math; P.ts[9] = e_issue;
+        }
+#undef KB_EP
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();  // the peer may still read this CTA's shared memory / signal its barriers
+    if (warp == 2) ptx::tmem_dealloc2(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -813,6 +1262,9 @@ int net_reserve(kb_net* net, int batch) {
 void* net_input_planes(kb_net* net) { return net->P; }
 int net_launches_per_forward(kb_net* net) { return net->fused ? 1 : (int)net->layers.size() + 2; }
 
+static long long* g_conv_ts = nullptr;  // profiling hook (kb_net_debug_timestamps)
+static int g_conv_ts_slot = 0;          // 16 counters per launch, 8 launches kept
+
 template <int N_TILE>
 static int launch_conv(const ConvParams& p, cudaStream_t st) {
     using C = ConvCfg<N_TILE>;
@@ -825,6 +1277,30 @@ static int launch_conv(const ConvParams& p, cudaStream_t st) {
     k_conv<N_TILE><<<grid, 256, C::SMEM, st>>>(p);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
+}
+
+template <int N_TILE>
+static int launch_conv2(const ConvParams& p, cudaStream_t st) {
+    using C = Conv2Cfg<N_TILE>;
+    static bool configured = false;
+    if (!configured) {
+        KB_CUDA(cudaFuncSetAttribute(k_conv2<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        configured = true;
+    }
+    const int pairs = (p.items + 1) / 2, max_pairs = sm_count() / 2;
+    const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+    k_conv2<N_TILE><<<grid, 384, C::SMEM, st>>>(p);  // cluster dims (2,1,1) are a kernel attribute
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+static bool use_pair_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KB_NO_PAIR_CONV");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 static int run_conv(const Layer& L, const uint4* in, uint4* out, const uint4* skip, float* out_f32, int boards, cudaStream_t st) {
@@ -844,6 +1320,16 @@ static int run_conv(const Layer& L, const uint4* in, uint4* out, const uint4* sk
     p.n_valid = L.n_valid;
     p.ntaps = L.ntaps;
     p.relu = L.relu;
+    {
+        static int skew = -1;
+        if (skew < 0) {
+            const char* e = getenv("KB_CONV_SKEW");
+            skew = e ? atoi(e) : 0;
+        }
+        p.skew = skew;
+    }
+    p.ts = g_conv_ts ? g_conv_ts + 16 * (g_conv_ts_slot++ % 8) : nullptr;
+    if (L.n_tile == 128 && out && L.relu && use_pair_kernel()) return launch_conv2<128>(p, st);
     if (L.n_tile == 64) return launch_conv<64>(p, st);
     if (L.n_tile == 128) return launch_conv<128>(p, st);
     if (L.n_tile == 80) return launch_conv<80>(p, st);
@@ -1213,15 +1699,17 @@ int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, in
     KB_REQUIRE_INIT();
     KB_ARG(net, "net");
     if (enable && !net->ts_dev) {
-        KB_CUDA(cudaMalloc(&net->ts_dev, 64 * sizeof(long long)));
-        KB_CUDA(cudaMemset(net->ts_dev, 0, 64 * sizeof(long long)));
+        KB_CUDA(cudaMalloc(&net->ts_dev, 128 * sizeof(long long)));
+        KB_CUDA(cudaMemset(net->ts_dev, 0, 128 * sizeof(long long)));
     }
+    kb::g_conv_ts = enable && !net->fused ? net->ts_dev : nullptr;  // per-layer kernels: MMA-thread wait counters
+    if (!out) kb::g_conv_ts_slot = 0;
     if (out && net->ts_dev) {
-        long long h[64];
+        long long h[128];
         KB_CUDA(cudaStreamSynchronize(main_stream()));
         KB_CUDA(cudaMemcpy(h, net->ts_dev, sizeof(h), cudaMemcpyDeviceToHost));
         int n = 0;
-        while (n < 60 && n < cap && h[n]) { out[n] = h[n]; ++n; }
+        while (n < (kb::g_conv_ts ? 128 : 60) && n < cap && (h[n] || kb::g_conv_ts)) { out[n] = h[n]; ++n; }
         if (count) *count = n;
     }
     if (!enable && net->ts_dev) {
