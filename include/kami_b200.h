@@ -181,6 +181,8 @@ typedef struct kb_phase_ms {
     float select, encode, tower, heads, expand, total;
 } kb_phase_ms;
 int kb_pool_last_phase_ms(kb_pool* p, kb_phase_ms* out);
+/* debug: per-tree cycle counters of the last batched select, 8 int64 per tree (see tree.cu) */
+int kb_pool_debug_select_profile(kb_pool* p, int enable, long long* out, int cap_trees);
 
 /* raw device memory helpers so that hosts without a CUDA runtime binding (ctypes) can keep
  * buffers resident */

@@ -136,6 +136,7 @@ _SIGS = {
     "kb_pool_reset_stats": (C.c_int, [_P]),
     "kb_pool_drain_samples": (C.c_int, [_P, C.c_int, _f32p, _f32p, _f32p, _i32p]),
     "kb_pool_last_phase_ms": (C.c_int, [_P, C.POINTER(PhaseMs)]),
+    "kb_pool_debug_select_profile": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int]),
     "kb_dev_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "kb_dev_free": (C.c_int, [_P]),
     "kb_dev_upload": (C.c_int, [_P, _P, C.c_size_t]),

@@ -75,7 +75,7 @@ template <int N_TILE>
 __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     using C = ConvCfg<N_TILE>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::uniform_warp_id(), lane = threadIdx.x & 31;
     const uint32_t bar0 = ptx::smem_u32(smem);
     auto b_full = [&](int s) { return bar0 + 8u * s; };
     auto b_empty = [&](int s) { return bar0 + 8u * (4 + s); };
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 3 && lane == 0) {
+    if (warp == 3) {
         // ===== A producer: one bulk copy per (item, pass, slab) job, double buffered =====
         for (int job = 0; job < total_jobs; ++job) {
             const int ii = job / jobs_per_item, rem = job - ii * jobs_per_item;
@@ -128,11 +128,14 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             const int buf = job & 1;
             ptx::mbar_wait(a_empty(buf), ((job >> 1) & 1) ^ 1);
-            ptx::mbar_arrive_expect_tx(a_full(buf), C::A_BYTES);
             const uint4* src = P.in + ((size_t)item * P.slabs_in + ks) * SLAB_U4;
-            ptx::bulk_g2s(a_smem + buf * C::A_BYTES, src, C::A_BYTES, a_full(buf));
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(a_full(buf), C::A_BYTES);
+                ptx::bulk_g2s(a_smem + buf * C::A_BYTES, src, C::A_BYTES, a_full(buf));
+            }
+            __syncwarp();
         }
-    } else if (warp == 0 && lane == 0) {
+    } else if (warp == 0) {
         // ===== B producer: weight blocks in consumption order through the stage ring =====
         int stage = 0, sphase = 0;
         for (int job = 0; job < total_jobs; ++job) {
@@ -141,16 +144,19 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
             const uint4* src = P.w + (size_t)(pass * kslices + ks) * P.ntaps * (C::B_BYTES / 16);
             for (int tap = 0; tap < P.ntaps; ++tap, src += C::B_BYTES / 16) {
                 ptx::mbar_wait(b_empty(stage), sphase ^ 1);
-                ptx::mbar_arrive_expect_tx(b_full(stage), C::B_BYTES);
-                ptx::bulk_g2s(b_smem + stage * C::B_STRIDE, src, C::B_BYTES, b_full(stage));
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(b_full(stage), C::B_BYTES);
+                    ptx::bulk_g2s(b_smem + stage * C::B_STRIDE, src, C::B_BYTES, b_full(stage));
+                }
+                __syncwarp();
                 if (++stage == C::NSTAGE) {
                     stage = 0;
                     sphase ^= 1;
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer: one thread drives the tensor core =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: converged warp, one elected thread drives the tensor core =====
         constexpr uint32_t idesc = ptx::idesc_bf16(128, N_TILE);
         int stage = 0, sphase = 0, acc_count = 0;
         const bool prof = P.ts && blockIdx.x == 0;
@@ -182,29 +188,33 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
                 ptx::tc_fence_after();
                 if (prof) w_b += clock64() - c0;
                 const uint32_t b_lo0 = ptx::sw128_lo(b_smem + stage * C::B_STRIDE);
-                uint32_t first = (ks | tap) == 0 ? 0u : 1u;
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
+                if (ptx::elect_one()) {
+                    uint32_t first = (ks | tap) == 0 ? 0u : 1u;
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
 #pragma unroll
-                    for (int mt = 0; mt < C::MT; ++mt) {
-                        const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * (16 * TALL_PITCH * LINE_BYTES / 16), a_hi);
-                        ptx::mma_bf16(d_base + mt * N_TILE, adesc, bdesc, idesc, first);
+                        for (int mt = 0; mt < C::MT; ++mt) {
+                            const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * (16 * TALL_PITCH * LINE_BYTES / 16), a_hi);
+                            ptx::mma_bf16(d_base + mt * N_TILE, adesc, bdesc, idesc, first);
+                        }
+                        first = 1u;
                     }
-                    first = 1u;
+                    ptx::mma_commit(b_empty(stage));
                 }
-                ptx::mma_commit(b_empty(stage));
+                __syncwarp();
                 if (++stage == C::NSTAGE) {
                     stage = 0;
                     sphase ^= 1;
                 }
             }
-            ptx::mma_commit(a_empty(buf));
-            if (ks == kslices - 1) {
-                ptx::mma_commit(t_full(acc));
-                ++acc_count;
+            if (ptx::elect_one()) {
+                ptx::mma_commit(a_empty(buf));
+                if (ks == kslices - 1) ptx::mma_commit(t_full(acc));
             }
+            __syncwarp();
+            if (ks == kslices - 1) ++acc_count;
         }
-        if (prof) {
+        if (prof && lane == 0) {
             P.ts[0] = clock64() - t_begin;
             P.ts[1] = w_t;
             P.ts[2] = w_a;
@@ -764,7 +774,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ FusedParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::uniform_warp_id(), lane = threadIdx.x & 31;
     const uint32_t s0 = ptx::smem_u32(smem);
     auto b_full = [&](int s) { return s0 + 8u * s; };
     auto b_empty = [&](int s) { return s0 + 8u * (8 + s); };
@@ -799,14 +809,17 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ===== producer =====
+    if (warp == 0) {
+        // ===== producer (converged warp, one elected lane issues) =====
         int stage = 0, sphase = 0;
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             ptx::mbar_wait(region_clean, ii & 1);
-            ptx::mbar_arrive_expect_tx(p_full, SLAB_BYTES);
-            ptx::bulk_g2s(region_s + SLAB_BYTES, P.planes + (size_t)item * IN_SLABS * SLAB_U4, SLAB_BYTES, p_full);
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(p_full, SLAB_BYTES);
+                ptx::bulk_g2s(region_s + SLAB_BYTES, P.planes + (size_t)item * IN_SLABS * SLAB_U4, SLAB_BYTES, p_full);
+            }
+            __syncwarp();
             const uint4* w = P.w;
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
@@ -814,8 +827,11 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 const uint32_t bytes = (uint32_t)(L.n_sub * LINE_BYTES);
                 for (int b = 0; b < nblocks; ++b) {
                     ptx::mbar_wait(b_empty(stage), sphase ^ 1);
-                    ptx::mbar_arrive_expect_tx(b_full(stage), bytes);
-                    ptx::bulk_g2s(ring_s + stage * FZ_STAGE, w, bytes, b_full(stage));
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(b_full(stage), bytes);
+                        ptx::bulk_g2s(ring_s + stage * FZ_STAGE, w, bytes, b_full(stage));
+                    }
+                    __syncwarp();
                     w += bytes / 16;
                     if (++stage == FZ_NSTAGE) {
                         stage = 0;
@@ -824,8 +840,8 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer (converged warp, one elected lane issues) =====
         int stage = 0, sphase = 0;
         uint32_t act_phase = 0;
         for (int ii = 0; ii < my_items; ++ii) {
@@ -852,17 +868,20 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                             ptx::mbar_wait(b_full(stage), sphase);
                             ptx::tc_fence_after();
                             const uint32_t b_lo0 = ptx::sw128_lo(ring_s + stage * FZ_STAGE);
-                            uint32_t first = (ks | tap) == 0 ? 0u : 1u;
-                            for (int kk = 0; kk < ksteps; ++kk) {
-                                const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
+                            if (ptx::elect_one()) {
+                                uint32_t first = (ks | tap) == 0 ? 0u : 1u;
+                                for (int kk = 0; kk < ksteps; ++kk) {
+                                    const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
 #pragma unroll
-                                for (int mt = 0; mt < 4; ++mt) {
-                                    const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * (16 * TALL_PITCH * LINE_BYTES / 16), a_hi);
-                                    ptx::mma_bf16(d_base + mt * n, adesc, bdesc, idesc, first);
+                                    for (int mt = 0; mt < 4; ++mt) {
+                                        const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * (16 * TALL_PITCH * LINE_BYTES / 16), a_hi);
+                                        ptx::mma_bf16(d_base + mt * n, adesc, bdesc, idesc, first);
+                                    }
+                                    first = 1u;
                                 }
-                                first = 1u;
+                                ptx::mma_commit(b_empty(stage));
                             }
-                            ptx::mma_commit(b_empty(stage));
+                            __syncwarp();
                             if (++stage == FZ_NSTAGE) {
                                 stage = 0;
                                 sphase ^= 1;
@@ -873,7 +892,8 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                             }
                         }
                     }
-                ptx::mma_commit(t_full);
+                if (ptx::elect_one()) ptx::mma_commit(t_full);
+                __syncwarp();
             }
             // the last layer's epilogue also signals act_ready (TMEM drained) -- consume it
             ptx::mbar_wait(act_ready, act_phase);

@@ -159,6 +159,7 @@ __device__ void tree_reset(const PoolDev& P, int t) {  // mcts.h:331-339
         c.n_hist = 0;
         c.leaf_nact = 0;
         c.traj_len = 0;
+        c.want_compact = 0;
         start_position(c.root_pos);
     }
     __syncwarp();
@@ -177,11 +178,15 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
     float turn = root_turn_of(pos);
     if (lane == 0) c.path[0] = cur;
     unsigned long long scanned = 0;
+    // One dependent memory round trip per level: a level's scan loads the children's node AND meta
+    // words (two independent coalesced loads); the winner's copies are then shuffled out of the lane
+    // that scored it, so the next level starts from registers instead of re-reading nodes[cur] /
+    // meta[cur] / meta[child].
+    Node tn = nodes[cur];
+    u32 m = meta[cur];
     for (;;) {
-        const u32 m = meta[cur];
         const int k = (int)(m >> 16);
         if (k == 0) break;
-        const Node tn = nodes[cur];
         float cpuct = P.cfg.cpuct;
         if (P.cfg.scale_cpuct_by_actions) cpuct = __fdiv_rn(cpuct, (float)k);
         const double sq = __dsqrt_rn((double)tn.n);
@@ -189,12 +194,15 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
         const float fpu = __fmul_rn(P.cfg.fpu, child_turn);  // (Q6) sign follows the child's turn
         double best = -1000.0;
         int bi = 0x7fffffff;
+        Node bch = Node{0, 0.0f, 0.0f, 0u};
+        u32 bcm = 0;
         unsigned unvisited = 0;
         for (int i0 = 0; i0 < k; i0 += 32) {
             const int i = i0 + lane;
             bool nov = false;
             if (i < k) {
                 const Node ch = nodes[tn.child0 + i];
+                const u32 cm = meta[tn.child0 + i];
                 nov = ch.n == 0;
                 const float q = ch.n > 0 ? __fdiv_rn(ch.w, (float)ch.n) : fpu;
                 const float pc = __fmul_rn(ch.p, cpuct);
@@ -203,6 +211,8 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
                 if (uct > best) {
                     best = uct;
                     bi = i;
+                    bch = ch;
+                    bcm = cm;
                 }
             }
             if (P.cfg.force_expand_unvisited && !unvisited) {
@@ -220,13 +230,26 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
                 bi = oi;
             }
         }
-        if (unvisited) bi = (int)unvisited - 1;  // mcts.h:226-231
         if (bi == 0x7fffffff || depth >= MAX_DEPTH) {
             raise(P, bi == 0x7fffffff ? KB_ERR_STATE : KB_ERR_CAPACITY);
             return false;
         }
-        const u32 child = tn.child0 + (u32)bi;
-        const int action = (int)(meta[child] & 0xFFFF);
+        u32 child;
+        if (unvisited) {  // mcts.h:226-231: the forced child is nobody's arg-max, read it
+            bi = (int)unvisited - 1;
+            child = tn.child0 + (u32)bi;
+            tn = nodes[child];
+            m = meta[child];
+        } else {          // lane (bi & 31) scored child bi and still holds its words
+            const int src = bi & 31;
+            child = tn.child0 + (u32)bi;
+            tn.n = __shfl_sync(0xffffffffu, bch.n, src);
+            tn.w = __shfl_sync(0xffffffffu, bch.w, src);
+            tn.p = __shfl_sync(0xffffffffu, bch.p, src);
+            tn.child0 = __shfl_sync(0xffffffffu, bch.child0, src);
+            m = __shfl_sync(0xffffffffu, bcm, src);
+        }
+        const int action = (int)(m & 0xFFFF);
         Pos nx;
         make_move<true>(pos, decode_action(pos, action), nx);
         if (lane == 0) {
@@ -241,12 +264,23 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
     }
     __syncwarp();
     if (lane == 0 && scanned) atomicAdd(&P.stats->children_scanned, scanned);
-    int reason = terminal_before_movegen(pos, c.hist, nh);
+    // A node is one move sequence from the game start, so its terminal status never changes: the
+    // first visit caches it in the (otherwise unused) child0 word of the childless node and the
+    // repeat visits the reference absorbs inside its while loop (selfplay.cpp:133) skip movegen.
+    const u32 tcache = tn.child0;
+    int reason = 0;
     float value = 0.0f;
     int n = 0;
-    if (!reason) {
-        n = warp_legal_actions(pos, s, c.leaf_act);
-        if (n == 0) value = no_moves_value(pos, &reason);
+    if (tcache & 0x80000000u) {
+        reason = 1;
+        value = (tcache & 3u) == 1u ? 1.0f : (tcache & 3u) == 2u ? -1.0f : 0.0f;
+    } else {
+        reason = terminal_before_movegen(pos, c.hist, nh);
+        if (!reason) {
+            n = warp_legal_actions(pos, s, c.leaf_act);
+            if (n == 0) value = no_moves_value(pos, &reason);
+        }
+        if (reason && lane == 0) nodes[cur].child0 = 0x80000000u | (value > 0.0f ? 1u : value < 0.0f ? 2u : 0u);
     }
     if (reason) {  // terminal leaf: back up the absolute value and report "no observation"
         warp_backprop(P, c, nodes, depth, value);
@@ -431,8 +465,11 @@ __device__ bool push_once(const PoolDev& P, int t, int action) {
     // Re-rooting is free (the root index moves); the copying collector only runs when the arena
     // could not hold another move's worth of expansions.
     const u32 reserve = P.cfg.selfplay_nodes > 0 && (u32)P.cfg.selfplay_nodes * 64u < P.cap / 2 ? (u32)P.cfg.selfplay_nodes * 64u : P.cap / 2;
-    if (c.alloc + reserve > P.cap) compact_into_other_space(P, t, keep);
-    else if (lane == 0) c.root = keep;
+    if (c.alloc + reserve > P.cap && !P.defer_compact) compact_into_other_space(P, t, keep);
+    else if (lane == 0) {
+        c.root = keep;
+        if (c.alloc + reserve > P.cap) c.want_compact = 1;
+    }
     __syncwarp();
     return true;
 }
@@ -551,13 +588,32 @@ __device__ void play_move(const PoolDev& P, int t, WarpScratch& s) {
         unsigned long long slot0 = 0;
         if (lane == 0) slot0 = atomicAdd(P.replay_head, (unsigned long long)len);
         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        for (int i = 0; i < len; ++i) {
-            const TrajSample* src = P.traj + (size_t)t * P.traj_cap + i;
-            ReplaySample* dst = P.replay + (slot0 + i) % (unsigned long long)P.replay_cap;
-            const uint4* s4 = reinterpret_cast<const uint4*>(src);
-            uint4* d4 = reinterpret_cast<uint4*>(&dst->s);
-            for (int j = lane; j < (int)(sizeof(TrajSample) / 16); j += 32) d4[j] = s4[j];
-            if (lane == 0) dst->z = value == 0.0f ? P.cfg.draw_value : __fmul_rn(src->pov, value);
+        {   // one flat copy of len samples (38 x 16 B each) with eight loads in flight per lane
+            constexpr int CH = (int)(sizeof(TrajSample) / 16);
+            const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(P.traj + (size_t)t * P.traj_cap);
+            const int total = len * CH;
+            for (int base = 0; base < total; base += 32 * 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + u * 32 + lane;
+                    if (e < total) v[u] = __ldg(s4 + e);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + u * 32 + lane;
+                    if (e < total) {
+                        const int i = e / CH, j = e - i * CH;
+                        ReplaySample* dst = P.replay + (slot0 + i) % (unsigned long long)P.replay_cap;
+                        reinterpret_cast<uint4*>(&dst->s)[j] = v[u];
+                    }
+                }
+            }
+            for (int i = lane; i < len; i += 32) {
+                const TrajSample* src = P.traj + (size_t)t * P.traj_cap + i;
+                ReplaySample* dst = P.replay + (slot0 + i) % (unsigned long long)P.replay_cap;
+                dst->z = value == 0.0f ? P.cfg.draw_value : __fmul_rn(src->pov, value);
+            }
         }
         if (lane == 0) {
             c.games += 1;
@@ -585,6 +641,88 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_reset(PoolDev P) 
     tree_reset(P, t);
 }
 
+// Block-cooperative copying collector for the batched loops (one block per tree, launched every
+// few steps at a safe point: no leaf pending).  Same breadth-first order as the warp version, so
+// the resulting arena is identical; 256 parents per wave, children copied as one flat range.
+__global__ void __launch_bounds__(256) k_pool_compact(PoolDev P) {
+    const int t = blockIdx.x;
+    TreeCtl& c = P.ctl[t];
+    if (!c.want_compact) return;
+    __shared__ u32 s_incl[256], s_oc[256], s_warp[8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const Node* __restrict__ sn = tree_nodes(P, t, c.space);
+    const u32* __restrict__ sm = tree_meta(P, t, c.space);
+    Node* dn = tree_nodes(P, t, c.space ^ 1);
+    u32* dm = tree_meta(P, t, c.space ^ 1);
+    const u32 keep = c.root;
+    if (tid == 0) {
+        dn[0] = sn[keep];
+        dm[0] = sm[keep];
+    }
+    __syncthreads();
+    u32 tail = 1, head = 0;
+    while (head < tail) {
+        const u32 wave = tail - head < 256u ? tail - head : 256u;
+        const u32 i = head + tid;
+        u32 k = 0, oc = 0;
+        if ((u32)tid < wave) {
+            k = dm[i] >> 16;
+            oc = dn[i].child0;
+        }
+        u32 incl = k;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        u32 before = 0;
+        for (int j = 0; j < w; ++j) before += s_warp[j];
+        incl += before;
+        s_incl[tid] = incl;
+        s_oc[tid] = oc;
+        if (k) dn[i].child0 = tail + incl - k;
+        __syncthreads();
+        const u32 total = s_incl[255];
+        for (u32 base = 0; base < total; base += 256 * 4) {
+            u32 src[4];
+            Node nv[4];
+            u32 mv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const u32 j = base + u * 256 + tid;
+                if (j < total) {
+                    int lo = 0;  // first parent whose inclusive child count exceeds j
+#pragma unroll
+                    for (int step = 128; step > 0; step >>= 1)
+                        if (s_incl[lo + step - 1] <= j) lo += step;
+                    src[u] = s_oc[lo] + j - (lo ? s_incl[lo - 1] : 0u);
+                    nv[u] = sn[src[u]];
+                    mv[u] = sm[src[u]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const u32 j = base + u * 256 + tid;
+                if (j < total) {
+                    dn[tail + j] = nv[u];
+                    dm[tail + j] = mv[u];
+                }
+            }
+        }
+        __syncthreads();
+        tail += total;
+        head += wave;
+    }
+    if (tid == 0) {
+        c.space ^= 1;
+        c.root = 0;
+        c.alloc = tail;
+        c.want_compact = 0;
+    }
+}
+
 // Batched select: the inner loop of selfplay.cpp:116-193 for every tree at once.
 // planes != nullptr: also writes the leaf's bf16 input planes (kernel 1 fused behind select).
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P, uint4* planes, Pos* leaf_out) {
@@ -594,19 +732,32 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P,
     if (t >= P.n_trees) return;
     WarpScratch& s = scratch[w];
     TreeCtl& c = P.ctl[t];
+    const bool prof = P.dbg != nullptr;
+    long long t_move = 0, t_sel = 0, t_enc = 0, n_sel = 0, n_move = 0, c0 = 0, t0 = prof ? clock64() : 0;
     for (int guard = 0; guard < (1 << 20); ++guard) {
         if (*P.error) return;
         if (P.cfg.selfplay_nodes > 0) {
             const int rn = tree_nodes(P, t, c.space)[c.root].n;
             if (rn >= P.cfg.selfplay_nodes) {
+                if (prof) c0 = clock64();
                 play_move(P, t, s);
+                if (prof) { t_move += clock64() - c0; ++n_move; }
                 continue;
             }
         }
-        if (select_once(P, t, s)) break;
+        if (prof) c0 = clock64();
+        const bool got = select_once(P, t, s);
+        if (prof) { t_sel += clock64() - c0; ++n_sel; }
+        if (got) break;
     }
+    if (prof) c0 = clock64();
     if (planes) warp_encode_tall(c.leaf_pos, t, planes);
     if (leaf_out && lane_id() == 0) leaf_out[t] = c.leaf_pos;
+    if (prof && lane_id() == 0) {
+        t_enc = clock64() - c0;
+        long long* d = P.dbg + (size_t)t * 8;
+        d[0] = clock64() - t0; d[1] = t_sel; d[2] = n_sel; d[3] = t_move; d[4] = n_move; d[5] = t_enc; d[6] = c.depth; d[7] = c.leaf_nact;
+    }
 }
 
 // Batched expand + backup.  value_stride/value_mode implement NN::infer's value indexing (Q1).
@@ -1126,6 +1277,7 @@ struct kb_pool {
     float* value_dev;    // [n][256]
     float* obs_batch_dev; // [n][1920] staging of the host-I/O path
     unsigned long long launches;
+    unsigned selects_since_compact;
     cudaEvent_t ev[6];
     kb_phase_ms last;
     unsigned long long replay_tail;
@@ -1242,7 +1394,7 @@ int kb_pool_destroy(kb_pool* p) {
     cudaFree(d.traj); cudaFree(d.replay); cudaFree(d.replay_head);
     cudaFree(p->obs_dev); cudaFree(p->pol_dev); cudaFree(p->int_dev); cudaFree(p->u64_dev); cudaFree(p->info_dev);
     cudaFree(p->child_i); cudaFree(p->child_f); cudaFree(p->leaf_dev); cudaFree(p->policy_dev); cudaFree(p->value_dev);
-    cudaFree(p->obs_batch_dev);
+    cudaFree(p->obs_batch_dev); cudaFree(d.dbg);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(p->ev[i]);
     delete p;
     return KB_OK;
@@ -1384,10 +1536,26 @@ int kb_tree_env(kb_pool* p, int tree, kb_position* out) {
 // ---- batched phases -------------------------------------------------------------------------
 static inline int pool_blocks(kb_pool* p) { return (p->d.n_trees + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
 
+// Select launch of the batched loops.  Arena compaction is deferred (push only flags a nearly full
+// arena; the reserve covers many more steps) and done by k_pool_compact every COMPACT_PERIOD selects.
+constexpr int COMPACT_PERIOD = 8;
+static int pool_launch_select(kb_pool* p, uint4* planes, Pos* leaf_out, cudaStream_t st) {
+    PoolDev d = p->d;
+    d.defer_compact = 1;
+    if (p->selects_since_compact++ % COMPACT_PERIOD == 0) {
+        k_pool_compact<<<d.n_trees, 256, 0, st>>>(d);
+        KB_CUDA(cudaGetLastError());
+        p->launches++;
+    }
+    k_pool_select<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(d, planes, leaf_out);
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
 int kb_pool_select(kb_pool* p) {
     KB_ARG(p, "pool");
-    k_pool_select<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, main_stream()>>>(p->d, nullptr, p->leaf_dev);
-    KB_CUDA(cudaGetLastError());
+    int r = pool_launch_select(p, nullptr, p->leaf_dev, main_stream());
+    if (r) return r;
     p->launches++;
     return pool_check(p, true);
 }
@@ -1425,8 +1593,7 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters) {
     for (int it = 0; it < iters; ++it) {
         const bool timed = it == iters - 1;
         if (timed) KB_CUDA(cudaEventRecord(p->ev[1], st));
-        k_pool_select<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, planes, nullptr);
-        KB_CUDA(cudaGetLastError());
+        if ((r = pool_launch_select(p, planes, nullptr, st))) return r;
         if (timed) KB_CUDA(cudaEventRecord(p->ev[2], st));
         r = net_forward_async(net, planes, n, p->policy_dev, p->value_dev, st);
         if (r) return r;
@@ -1460,8 +1627,7 @@ int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, flo
     if (r) return r;
     for (int it = 0; it < iters; ++it) {
         // select + Env::observe on the device, observations out to the caller's buffer
-        k_pool_select<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, nullptr, p->leaf_dev);
-        KB_CUDA(cudaGetLastError());
+        if ((r = pool_launch_select(p, nullptr, p->leaf_dev, st))) return r;
         if ((r = kb_encode_planes_dev((const kb_position*)p->leaf_dev, (int)n, p->obs_batch_dev))) return r;
         KB_CUDA(cudaMemcpyAsync(obs_host, p->obs_batch_dev, sizeof(float) * KB_OBSIZE * n, cudaMemcpyDeviceToHost, st));
         if ((r = pool_check(p, true))) return r;
@@ -1506,6 +1672,27 @@ int kb_pool_reset_stats(kb_pool* p) {
     p->launches = 0;
     return KB_OK;
 }
+// Debug hook: per-tree cycle counters of the last select kernel: [total, select cycles, select calls,
+// play_move cycles, moves, encode cycles, leaf depth, leaf actions].  enable allocates the buffer.
+int kb_pool_debug_select_profile(kb_pool* p, int enable, long long* out, int cap_trees) {
+    KB_ARG(p, "pool");
+    if (enable && !p->d.dbg) {
+        KB_CUDA(cudaMalloc(&p->d.dbg, sizeof(long long) * 8 * (size_t)p->d.n_trees));
+        KB_CUDA(cudaMemset(p->d.dbg, 0, sizeof(long long) * 8 * (size_t)p->d.n_trees));
+    }
+    if (out && p->d.dbg) {
+        KB_CUDA(cudaStreamSynchronize(main_stream()));
+        const int n = cap_trees < p->d.n_trees ? cap_trees : p->d.n_trees;
+        KB_CUDA(cudaMemcpy(out, p->d.dbg, sizeof(long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    if (!enable && p->d.dbg) {
+        cudaStreamSynchronize(main_stream());
+        cudaFree(p->d.dbg);
+        p->d.dbg = nullptr;
+    }
+    return KB_OK;
+}
+
 int kb_pool_last_phase_ms(kb_pool* p, kb_phase_ms* out) {
     KB_ARG(p && out, "pool/out");
     *out = p->last;

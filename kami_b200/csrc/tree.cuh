@@ -69,6 +69,8 @@ struct TreeCtl {
     int n_hist;  // game keys in hist[]; path keys follow
     int leaf_nact;
     int traj_len;
+    u32 want_compact;  // the arena is nearly full: k_pool_compact moves the live subtree at the next safe point
+    u32 pad_;
     u64 rng;
     u64 games, moves;
     u16 leaf_act[MAX_MOVES];
@@ -94,6 +96,8 @@ struct PoolDev {
     int replay_cap;
     unsigned long long* replay_head;
     Cfg cfg;
+    long long* dbg;     // optional [n_trees][8] cycle counters of the last k_pool_select (kb_pool_debug_select_profile)
+    int defer_compact;  // batched loops: push only flags a full arena, k_pool_compact (a block per tree) copies
 };
 
 struct WarpScratch {

@@ -47,7 +47,7 @@ def test_reference_nn_and_mcts_programs_run(kb):
     text = out.stdout.decode()
     assert text.count("pred/s") == 5 and "aborting" not in text
     try:
-        out = subprocess.run([os.path.join(DROPIN, "test_bench")], capture_output=True, timeout=15)
+        out = subprocess.run([os.path.join(DROPIN, "test_bench")], capture_output=True, timeout=60)
         text = out.stdout.decode()
     except subprocess.TimeoutExpired as e:
         text = (e.stdout or b"").decode()

@@ -202,6 +202,43 @@ def test_pool_batched_select_expand_vs_oracle(kb):
         assert pool.tree(i).digest() == orc[i].digest()
 
 
+def test_pool_selfplay_moves_with_deferred_compaction_vs_oracle(kb):
+    """The budget branch of Selfplay::inference_main (selfplay.cpp:136-192) inside k_pool_select: argmax
+    pick (alpha < 0.1), push with subtree reuse, reset at game end -- on arenas so small that the
+    block-cooperative collector (k_pool_compact, deferred to every 8th select) runs many times.  Every
+    leaf must equal the leaf of an oracle tree driven through the same loop with the same NN outputs."""
+    nodes, n = 24, 12
+    cfg = dict(noise_weight=0.0, **H.DEF_YML)
+    pool = kb.TreePool(n, 1 << 12, _cfg(kb, selfplay_nodes=nodes, alpha_initial=0.0, alpha_decay=1.0, alpha_final=0.0,
+                                        alpha_cutoff=0, **cfg))
+    orc = [H.OracleMcts(H.default_cfg(**cfg)) for _ in range(n)]
+    rng = np.random.RandomState(11)
+    moves = 0
+    for it in range(600):
+        pool.select()
+        leaves = pool.leaf_positions()
+        pol = rng.rand(n, H.PSIZE).astype(np.float32)
+        pol /= pol.sum(1, keepdims=True)
+        val = (rng.rand(n) * 2 - 1).astype(np.float32)
+        for i, o in enumerate(orc):
+            while True:
+                if o.n() >= nodes:
+                    o.push(o.pick(0.0))
+                    moves += 1
+                    if o.env.terminal()[0]:
+                        o.reset()
+                    continue
+                if o.select()[0]:
+                    break
+            assert np.array_equal(leaves[i:i + 1].view(np.uint8).reshape(-1), o.env.export()), (it, i)
+            o.expand(pol[i], float(val[i]))
+        pool.expand(pol, val)
+    st = pool.stats()
+    assert st["moves"] == moves and moves > 40 * n
+    for i in (0, 5, n - 1):
+        assert pool.tree(i).digest() == orc[i].digest()
+
+
 # ---- network ---------------------------------------------------------------------------------------
 def _kl(p, q):
     return float((p * (np.log(p + 1e-30) - np.log(q + 1e-30))).sum(1).max())
