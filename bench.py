@@ -35,6 +35,7 @@ TREES_PER_GPU = 1024
 FILTERS, RESIDUALS = 64, 2          # options.def.yml:29,53
 SELFPLAY_NODES = 1024               # options.def.yml selfplay_nodes
 NODE_CAPACITY = 1 << 19  # 2 x 10 MB per tree: the copying collector runs about once per 40 moves
+TOWER64_DRAM_BYTES_PER_LAUNCH = 12606720  # profiles/r01_ncu_summary_v2.txt
 PREROLL_STEPS = 1536                # untimed: grows the synthetic trees to steady state (first moves made)
 METRIC = "selfplay_nn_evals_per_sec"
 UNIT = "evals/s"
@@ -310,9 +311,13 @@ def run_ours(args, rank, world, local, dist):
     dominant = max(phases, key=phases.get)
     if dominant == "tower+heads":
         achieved = (t_f + h_f) * TREES_PER_GPU / (ph["tower"] * 1e-3) / 1e12
-        roof = {"kernel": "k_conv x%d + heads (tcgen05 tower, %dx%d)" % (1 + 2 * RESIDUALS + 2, RESIDUALS, FILTERS),
+        roof = {"kernel": "k_tower64 (one fused tcgen05 launch: %dx%d tower + policy/value heads + softmax)" % (RESIDUALS, FILTERS),
                 "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                "traffic": None, "peak_kind": peak_kind + " burst",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one k_tower64 launch at 1024 boards, from the
+                # ncu --set full capture summarised in profiles/r01_ncu_summary_v2.txt (12.607 MB read: 147 input
+                # slabs of 80 KB + weights; the 19 MB policy rows stay in L2 for k_pool_expand)
+                "traffic": TOWER64_DRAM_BYTES_PER_LAUNCH if TREES_PER_GPU == 1024 else None,
+                "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst",
                 "algorithmic": "%.3f MFLOP/position x %d positions per launch group" % ((t_f + h_f) / 1e6, TREES_PER_GPU)}
     else:
         per_step = (12.0 * st["children_scanned"] + 16.0 * st["path_nodes"] + 16.0 * st["children_created"]) / max(1, args.steps)
