@@ -173,6 +173,9 @@ typedef struct kb_pool_stats {
 } kb_pool_stats;
 int kb_pool_get_stats(kb_pool* p, kb_pool_stats* out);
 int kb_pool_reset_stats(kb_pool* p);
+/* kb_pool_step policy path: 0 (default) = softmax over each leaf's legal moves only, fused behind the policy head and
+ * equal to nn.cpp:80 followed by MCTS::expand's renormalisation (mcts.h:273-276,296); 1 = dense [n][4672] softmax */
+int kb_pool_set_policy_mode(kb_pool* p, int dense);
 /* replay sink: finished-game samples (selfplay.cpp:141-188) kept on the device as sparse rows */
 int kb_pool_drain_samples(kb_pool* p, int max_samples, float* obs /*[m][1920]*/, float* pi /*[m][4672]*/, float* z /*[m]*/, int* count);
 

@@ -134,6 +134,7 @@ _SIGS = {
     "kb_pool_step_hostio": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "kb_pool_get_stats": (C.c_int, [_P, C.POINTER(PoolStats)]),
     "kb_pool_reset_stats": (C.c_int, [_P]),
+    "kb_pool_set_policy_mode": (C.c_int, [_P, C.c_int]),
     "kb_pool_drain_samples": (C.c_int, [_P, C.c_int, _f32p, _f32p, _f32p, _i32p]),
     "kb_pool_last_phase_ms": (C.c_int, [_P, C.POINTER(PhaseMs)]),
     "kb_pool_debug_select_profile": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int]),
@@ -418,6 +419,10 @@ class TreePool:
 
     def reset_stats(self):
         _ck(self.L.kb_pool_reset_stats(self.h))
+
+    def set_policy_mode(self, dense):
+        """0: softmax over the legal moves only (default); 1: dense softmax over all 4672 actions."""
+        _ck(self.L.kb_pool_set_policy_mode(self.h, int(dense)))
 
     def phase_ms(self):
         s = PhaseMs()

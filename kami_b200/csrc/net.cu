@@ -756,6 +756,11 @@ struct FusedParams {
     const float* fcb;
     int* nan_flag;
     long long* ts;  // optional per-phase clock64 stamps of CTA 0 (profiling hook), or nullptr
+    // legal-gather mode (pool step): per-board action lists instead of the dense softmax
+    const uint8_t* legal_act;
+    const uint8_t* legal_n;
+    unsigned long long legal_stride;
+    float* prior;
     float bv;
     int n_bias, items, boards, n_layers, tower_layers;
     FusedLayer layer[16];
@@ -1043,7 +1048,35 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
             // ---- softmax over the 4672 logits of each board (nn.cpp:80) ----
             epi_bar();
             KB_STAMP();
-            {
+            if (P.legal_act) {
+                // ---- softmax numerators over the legal moves only: warp e gathers board e's logits ----
+                const float* lg = reinterpret_cast<const float*>(region);
+                const int board = item * NB + e;
+                if (e < NB && board < P.boards) {
+                    const int n = *reinterpret_cast<const int*>(P.legal_n + (size_t)board * P.legal_stride);
+                    const uint16_t* acts = reinterpret_cast<const uint16_t*>(P.legal_act + (size_t)board * P.legal_stride);
+                    float l[4];
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int i = lane + 32 * r;
+                        l[r] = i < n ? lg[e * KB_PSIZE + acts[i]] : -INFINITY;
+                        m = fmaxf(m, l[r]);
+                    }
+                    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                    bool bad = false;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int i = lane + 32 * r;
+                        if (i < n) {
+                            const float o = __expf(l[r] - m);
+                            bad |= (o != o);
+                            P.prior[(size_t)board * 128 + i] = o;
+                        }
+                    }
+                    if (bad) atomicExch(P.nan_flag, 1);
+                }
+            } else {
                 // every thread owns 19 logits of each of the 7 boards; two block-wide reductions in total
                 float* red = vbuf;  // [8 warps][7] maxima, then [8][7] sums (the value head is done with vbuf)
                 const float* lg = reinterpret_cast<const float*>(region);
@@ -1207,6 +1240,37 @@ __global__ void __launch_bounds__(256) k_softmax(float* logits, int boards, int*
     if (bad) atomicExch(nan_flag, 1);
 }
 
+// Legal-gather for the per-layer path: one warp per board turns fp32 logits [board][4672] into
+// softmax numerators over that board's legal actions (see net_forward_legal_async).
+__global__ void __launch_bounds__(256) k_legal_prior(const float* logits, int boards, const uint8_t* act_base, const uint8_t* nact_base,
+                                                      unsigned long long stride, float* prior, int* nan_flag) {
+    const int board = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (board >= boards) return;
+    const int n = *reinterpret_cast<const int*>(nact_base + (size_t)board * stride);
+    const uint16_t* acts = reinterpret_cast<const uint16_t*>(act_base + (size_t)board * stride);
+    const float* lg = logits + (size_t)board * KB_PSIZE;
+    float l[4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = lane + 32 * r;
+        l[r] = i < n ? lg[acts[i]] : -INFINITY;
+        m = fmaxf(m, l[r]);
+    }
+    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = lane + 32 * r;
+        if (i < n) {
+            const float o = __expf(l[r] - m);
+            bad |= (o != o);
+            prior[(size_t)board * 128 + i] = o;
+        }
+    }
+    if (bad) atomicExch(nan_flag, 1);
+}
+
 }  // namespace kb
 
 // ==========================================================================================
@@ -1253,6 +1317,8 @@ struct kb_net {
     uint4* fused_w = nullptr;
     float* fused_bias = nullptr;
     long long* ts_dev = nullptr;
+    float* logits_dev = nullptr;  // [cap][4672] scratch of the legal-gather mode (per-layer path)
+    int logits_cap = 0;
 };
 
 namespace kb {
@@ -1357,7 +1423,31 @@ static int run_conv(const Layer& L, const uint4* in, uint4* out, const uint4* sk
     return KB_ERR_UNSUPPORTED;
 }
 
-int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, cudaStream_t st) {
+static int net_stage_logits(kb_net* net, int batch, float** out) {
+    if (batch > net->logits_cap) {
+        cudaStreamSynchronize(main_stream());
+        cudaFree(net->logits_dev);
+        net->logits_dev = nullptr;
+        net->logits_cap = 0;
+        if (cudaMalloc(&net->logits_dev, sizeof(float) * KB_PSIZE * (size_t)batch) != cudaSuccess) {
+            set_error("out of device memory for the logits scratch");
+            return 1;
+        }
+        net->logits_cap = batch;
+    }
+    *out = net->logits_dev;
+    return 0;
+}
+
+struct LegalRef {
+    const uint8_t* act = nullptr;
+    const uint8_t* nact = nullptr;
+    size_t stride = 0;
+    float* prior = nullptr;
+};
+
+static int net_forward_impl(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, const LegalRef& lr,
+                            cudaStream_t st) {
     if (!net->loaded) {
         set_error("network weights not loaded");
         return KB_ERR_STATE;
@@ -1377,12 +1467,20 @@ int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_
         fp.value256 = value256_dev;
         fp.nan_flag = net->nan_flag;
         fp.ts = net->ts_dev;
+        fp.legal_act = lr.act;
+        fp.legal_n = lr.nact;
+        fp.legal_stride = lr.stride;
+        fp.prior = lr.prior;
         fp.items = items_for(batch);
         fp.boards = batch;
         const int grid = fp.items < sm_count() ? fp.items : sm_count();
         k_tower64<<<grid, 384, FZ_SMEM, st>>>(fp);
         KB_CUDA(cudaGetLastError());
         return KB_OK;
+    }
+    float* logits = policy_dev;
+    if (lr.act) {  // the dense logits are scratch in legal mode
+        if (net_stage_logits(net, batch, &logits)) return KB_ERR_CUDA;
     }
     size_t li = 0;
     if ((r = run_conv(net->layers[li++], in, net->X, nullptr, nullptr, batch, st))) return r;
@@ -1391,12 +1489,29 @@ int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_
         if ((r = run_conv(net->layers[li++], net->Y, net->X, net->X, nullptr, batch, st))) return r;  // x = skip + relu(...)
     }
     if ((r = run_conv(net->layers[li++], net->X, net->H, nullptr, nullptr, batch, st))) return r;
-    if ((r = run_conv(net->layers[li++], net->H, nullptr, nullptr, policy_dev, batch, st))) return r;
-    k_softmax<<<batch, 256, 0, st>>>(policy_dev, batch, net->nan_flag);
+    if ((r = run_conv(net->layers[li++], net->H, nullptr, nullptr, logits, batch, st))) return r;
+    if (lr.act)
+        k_legal_prior<<<(batch + 7) / 8, 256, 0, st>>>(logits, batch, lr.act, lr.nact, lr.stride, lr.prior, net->nan_flag);
+    else
+        k_softmax<<<batch, 256, 0, st>>>(logits, batch, net->nan_flag);
     KB_CUDA(cudaGetLastError());
     k_value_head<<<batch, 256, 0, st>>>(net->X, (net->filters + 63) / 64, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, net->nan_flag);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
+}
+
+int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, cudaStream_t st) {
+    return net_forward_impl(net, planes, batch, policy_dev, value256_dev, LegalRef{}, st);
+}
+
+int net_forward_legal_async(kb_net* net, const void* planes, int batch, const void* act_base, const void* nact_base, size_t stride,
+                            float* prior_dev, float* value256_dev, cudaStream_t st) {
+    LegalRef lr;
+    lr.act = reinterpret_cast<const uint8_t*>(act_base);
+    lr.nact = reinterpret_cast<const uint8_t*>(nact_base);
+    lr.stride = stride;
+    lr.prior = prior_dev;
+    return net_forward_impl(net, planes, batch, nullptr, value256_dev, lr, st);
 }
 
 }  // namespace kb
@@ -1487,7 +1602,7 @@ int kb_net_destroy(kb_net* n) {
     cudaFree(n->wv); cudaFree(n->fct); cudaFree(n->fcb);
     cudaFree(n->P); cudaFree(n->X); cudaFree(n->Y); cudaFree(n->H);
     cudaFree(n->nan_flag); cudaFree(n->obs_dev); cudaFree(n->pol_dev); cudaFree(n->val_dev);
-    cudaFree(n->fused_w); cudaFree(n->fused_bias); cudaFree(n->ts_dev);
+    cudaFree(n->fused_w); cudaFree(n->fused_bias); cudaFree(n->ts_dev); cudaFree(n->logits_dev);
     delete n;
     return KB_OK;
 }

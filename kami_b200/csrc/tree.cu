@@ -298,7 +298,8 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
 }
 
 // MCTS::expand (mcts.h:257-327)
-__device__ void expand_once(const PoolDev& P, int t, const float* policy, float value, bool disable_bootstrap, WarpScratch& s) {
+// compact: policy[i] is already the (unnormalised) prior of the i-th legal action (net_forward_legal_async)
+__device__ void expand_once(const PoolDev& P, int t, const float* policy, float value, bool disable_bootstrap, WarpScratch& s, bool compact = false) {
     const int lane = lane_id();
     TreeCtl& c = P.ctl[t];
     if (c.state != 1) {
@@ -316,7 +317,7 @@ __device__ void expand_once(const PoolDev& P, int t, const float* policy, float 
     }
     const float nw = P.cfg.noise_weight;
     for (int i = lane; i < n; i += 32) {
-        s.fbuf[i] = policy[c.leaf_act[i]];
+        s.fbuf[i] = compact ? policy[i] : policy[c.leaf_act[i]];
         // (Q9) Exp(1) noise at every expansion; the reference's is time-seeded so only the
         // distribution can be matched.  With noise_weight == 0 the term is exactly +0.
         float nz = 1.0f;
@@ -761,7 +762,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P,
 }
 
 // Batched expand + backup.  value_stride/value_mode implement NN::infer's value indexing (Q1).
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P, const float* policy, const float* value, int value_is_256, int disable_bootstrap) {
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P, const float* policy, const float* value, int value_is_256, int disable_bootstrap,
+                                                                      int compact) {
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
     const int w = threadIdx.x >> 5;
     const int t = blockIdx.x * WARPS_PER_BLOCK + w;
@@ -770,7 +772,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P,
     float v;
     if (!value_is_256) v = value[t];
     else v = P.cfg.value_index_mode == 0 ? value[t] /* vh.flat[t], nn.cpp:186 */ : value[(size_t)t * 256];
-    expand_once(P, t, policy + (size_t)t * PSIZE, v, disable_bootstrap != 0, scratch[w]);
+    expand_once(P, t, policy + (size_t)t * (compact ? 128 : PSIZE), v, disable_bootstrap != 0, scratch[w], compact != 0);
 }
 
 // Single-tree entry points (the kami::MCTS call protocol)
@@ -1278,6 +1280,7 @@ struct kb_pool {
     float* obs_batch_dev; // [n][1920] staging of the host-I/O path
     unsigned long long launches;
     unsigned selects_since_compact;
+    int policy_mode;  // kb_pool_step: 0 softmax over the legal moves only (default), 1 dense [n][4672] softmax
     cudaEvent_t ev[6];
     kb_phase_ms last;
     unsigned long long replay_tail;
@@ -1566,7 +1569,7 @@ int kb_pool_leaf_positions(kb_pool* p, kb_position* out) {
 }
 int kb_pool_expand_dev(kb_pool* p, const float* policy_dev, const float* value_dev, int disable_bootstrap) {
     KB_ARG(p && policy_dev && value_dev, "pool/policy/value");
-    k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, main_stream()>>>(p->d, policy_dev, value_dev, 0, disable_bootstrap);
+    k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, main_stream()>>>(p->d, policy_dev, value_dev, 0, disable_bootstrap, 0);
     KB_CUDA(cudaGetLastError());
     p->launches++;
     return KB_OK;
@@ -1589,16 +1592,20 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters) {
     if (r) return r;
     cudaStream_t st = main_stream();
     uint4* planes = reinterpret_cast<uint4*>(net_input_planes(net));
+    const bool legal = p->policy_mode == 0;
     KB_CUDA(cudaEventRecord(p->ev[0], st));
     for (int it = 0; it < iters; ++it) {
         const bool timed = it == iters - 1;
         if (timed) KB_CUDA(cudaEventRecord(p->ev[1], st));
         if ((r = pool_launch_select(p, planes, nullptr, st))) return r;
         if (timed) KB_CUDA(cudaEventRecord(p->ev[2], st));
-        r = net_forward_async(net, planes, n, p->policy_dev, p->value_dev, st);
+        if (legal)  // softmax over the legal moves only: priors straight into p->policy_dev[tree][128]
+            r = net_forward_legal_async(net, planes, n, &p->d.ctl[0].leaf_act[0], &p->d.ctl[0].leaf_nact, sizeof(TreeCtl), p->policy_dev, p->value_dev, st);
+        else
+            r = net_forward_async(net, planes, n, p->policy_dev, p->value_dev, st);
         if (r) return r;
         if (timed) KB_CUDA(cudaEventRecord(p->ev[3], st));
-        k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 1, 0);
+        k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 1, 0, legal ? 1 : 0);
         KB_CUDA(cudaGetLastError());
         if (timed) KB_CUDA(cudaEventRecord(p->ev[4], st));
         p->launches += 2 + (unsigned long long)net_launches_per_forward(net);
@@ -1641,7 +1648,7 @@ int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, flo
         // MCTS::expand(host policy row, value)
         KB_CUDA(cudaMemcpyAsync(p->policy_dev, policy_host, sizeof(float) * KB_PSIZE * n, cudaMemcpyHostToDevice, st));
         KB_CUDA(cudaMemcpyAsync(p->value_dev, value_host, sizeof(float) * n, cudaMemcpyHostToDevice, st));
-        k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 0, 0);
+        k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 0, 0, 0);
         KB_CUDA(cudaGetLastError());
         p->launches += 4 + (unsigned long long)net_launches_per_forward(net);
     }
@@ -1690,6 +1697,12 @@ int kb_pool_debug_select_profile(kb_pool* p, int enable, long long* out, int cap
         cudaFree(p->d.dbg);
         p->d.dbg = nullptr;
     }
+    return KB_OK;
+}
+
+int kb_pool_set_policy_mode(kb_pool* p, int dense) {
+    KB_ARG(p && (dense == 0 || dense == 1), "pool/mode");
+    p->policy_mode = dense;
     return KB_OK;
 }
 

@@ -386,6 +386,7 @@ def test_pool_step_matches_hostio_path(kb):
     net.load_blob(NO.pack_blob(params, F, R))
     kw = dict(noise_weight=0.0, selfplay_nodes=16, seed=1, **H.DEF_YML)
     a, b = kb.TreePool(n, 1 << 14, _cfg(kb, **kw)), kb.TreePool(n, 1 << 14, _cfg(kb, **kw))
+    a.set_policy_mode(1)  # dense softmax, the arithmetic of the host round trip
     a.step(net, 60)
     obs = np.zeros((n, 1920), np.float32)
     pol = np.zeros((n, H.PSIZE), np.float32)
@@ -394,3 +395,28 @@ def test_pool_step_matches_hostio_path(kb):
     for i in (0, 5, n - 1):
         assert a.tree(i).digest() == b.tree(i).digest()
     assert a.stats()["moves"] == b.stats()["moves"]
+
+
+@pytest.mark.parametrize("F,R", [(64, 2), (128, 1)])
+def test_pool_step_legal_softmax_equals_dense_softmax_renormalised(kb, F, R):
+    """kb_pool_step's default policy path (softmax over the legal moves only, fused behind the policy head:
+    north_star kernel 3) against the dense softmax + MCTS::expand renormalisation (nn.cpp:80, mcts.h:273-296):
+    same children, priors equal to fp32 rounding, same visit counts over a short search."""
+    n = 40
+    params = NO.init_params(F, R, seed=6)
+    net = kb.NN(F, R)
+    net.load_blob(NO.pack_blob(params, F, R))
+    kw = dict(noise_weight=0.0, selfplay_nodes=0, seed=1, **H.DEF_YML)
+    a, b = kb.TreePool(n, 1 << 14, _cfg(kb, **kw)), kb.TreePool(n, 1 << 14, _cfg(kb, **kw))
+    b.set_policy_mode(1)
+    a.step(net, 1)
+    b.step(net, 1)
+    for i in (0, 7, n - 1):
+        aa, an, aw, ap = a.tree(i).root_children()
+        ba, bn, bw, bp = b.tree(i).root_children()
+        assert np.array_equal(aa, ba) and len(aa) == 20
+        assert np.abs(ap - bp).max() <= 2e-6 and abs(float(ap.sum()) - 1.0) < 1e-5
+    a.step(net, 24)
+    b.step(net, 24)
+    same = sum(np.array_equal(a.tree(i).root_children()[1], b.tree(i).root_children()[1]) for i in range(n))
+    assert same >= n - 2  # a prior that differs in the last bit may flip an exact PUCT tie
