@@ -6,6 +6,7 @@
 // (c) time the reference's CPU NN::infer in bench.py's reference arm.
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <string>
 #include <vector>
 
@@ -75,6 +76,27 @@ int ref_nn_forward_full(void* p, float* input, int batch, float* policy, float* 
     memcpy(policy, ph.data_ptr<float>(), sizeof(float) * batch * 4672);
     memcpy(value256, vh.data_ptr<float>(), sizeof(float) * batch * 256);
     return 0;
+}
+
+// NN::train (kami/nn/nn.cpp:224-377) with the reference's own option keys: training_mlr (lr*1000),
+// training_epochs, training_batchsize.  Leaves the module in eval mode with generation + 1.
+int ref_nn_train(void* p, int n, float* inputs, float* obs_p, float* obs_v, int mlr, int epochs, int batchsize) {
+    options::setInt("training_mlr", mlr);
+    options::setInt("training_epochs", epochs);
+    options::setInt("training_batchsize", batchsize);
+    Handle* h = (Handle*)p;
+    // NN::train prints progress with operator<<(int/float); inside a Python process whose libstdc++
+    // locale facets come from another copy of the library that crashes, so mute the stream meanwhile
+    std::cout.setstate(std::ios_base::failbit);
+    try {
+        h->nn->train(n, inputs, obs_p, obs_v, false);
+    } catch (std::exception& e) {
+        std::cout.clear();
+        return -1;
+    }
+    std::cout.clear();
+    collect(h);
+    return h->nn->get_generation();
 }
 
 int ref_nn_num_tensors(void* p) { return (int)((Handle*)p)->tensors.size(); }

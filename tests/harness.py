@@ -401,6 +401,7 @@ def ref_nn_lib():
         L.ref_nn_tensor_get.argtypes = [C.c_void_p, C.c_int, c_float_p]
         L.ref_nn_tensor_set.argtypes = [C.c_void_p, C.c_int, c_float_p]
         L.ref_nn_set_threads.argtypes = [C.c_int]
+        L.ref_nn_train.argtypes = [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
         _refnn = L
     return _refnn
 
@@ -461,6 +462,16 @@ class RefNN:
         val = np.zeros((B, 256), np.float32)
         self.L.ref_nn_forward_full(self.h, _fp(obs), B, _fp(pol), _fp(val))
         return pol, val
+
+    def train(self, obs, obs_p, obs_v, mlr, epochs, batchsize):
+        """NN::train (nn.cpp:224-377); returns the new generation."""
+        obs = np.ascontiguousarray(obs, np.float32)
+        obs_p = np.ascontiguousarray(obs_p, np.float32)
+        obs_v = np.ascontiguousarray(obs_v, np.float32)
+        g = self.L.ref_nn_train(self.h, len(obs_v), _fp(obs), _fp(obs_p), _fp(obs_v), mlr, epochs, batchsize)
+        if g < 0:
+            raise RuntimeError("reference NN::train threw")
+        return g
 
 
 def sample_positions(n, seed=0, max_ply=120):
