@@ -201,6 +201,27 @@ int kb_timer_start(void);
 int kb_timer_stop(float* ms);
 int kb_flush_l2(size_t bytes);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step: NN::train's mini-batch (kami/nn/nn.cpp:224-377) = NNModule::forward in
+ * training mode (BatchNorm batch statistics), NNModule::loss (nn.cpp:93-105), backward, plain SGD
+ * (nn.cpp:239-241).  fp32 master weights / gradients / running statistics in the blob order of
+ * kb_net_load_blob; bf16 tcgen05 convolutions (forward, dgrad, wgrad).  Data-parallel hosts all-reduce
+ * the buffer kb_trainer_grad_buffer returns (NCCL) between forward_backward and apply_sgd.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kb_trainer kb_trainer;
+int kb_trainer_create(kb_trainer** out, int filters, int residuals, int max_batch);
+int kb_trainer_destroy(kb_trainer* t);
+int kb_trainer_load_blob(kb_trainer* t, const float* blob, size_t n_floats);
+int kb_trainer_export_blob(kb_trainer* t, float* blob, size_t n_floats);
+int kb_trainer_export_grads(kb_trainer* t, float* out, size_t n_floats);
+int kb_trainer_grad_buffer(kb_trainer* t, void** dev_ptr, size_t* n_floats);
+/* inputs [batch][1920], obs_p [batch][4672], obs_v [batch]: the arrays of NN::train (nn.h:67); host pointers */
+int kb_trainer_forward_backward(kb_trainer* t, const float* obs, const float* obs_p, const float* obs_v, int batch, float* loss);
+int kb_trainer_forward_backward_dev(kb_trainer* t, const float* obs_dev, const float* obs_p_dev, const float* obs_v_dev, int batch, float* loss);
+int kb_trainer_apply_sgd(kb_trainer* t, float lr, float grad_scale);
+/* test hook: one board of a saved training activation, fp32 [channels][64] (which: 0 conv output, 1 layer output) */
+int kb_trainer_debug_activation(kb_trainer* t, int layer, int which, int board, float* out, int* channels);
+
 #ifdef __cplusplus
 }
 #endif

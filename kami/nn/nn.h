@@ -2,6 +2,7 @@
 // LibTorch.  Forward runs as the tcgen05 kernels of libkami_b200; weights are a flat fp32 blob
 // in the reference's parameter naming (oracle/nn_oracle.py:param_order).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -107,8 +108,66 @@ class NN {
         if (rc == KB_ERR_NAN) throw std::runtime_error("inference policy output contains NaN");
         check(rc);
     }
-    void train(int, float*, float*, float*, bool = false) {
-        throw std::runtime_error("NN::train is not built yet (SURVEY.md 8(f) #1: train step + NCCL all-reduce)");
+    // nn.cpp:224-377: `epochs` passes of shuffled mini-batches of `training_batchsize`, plain SGD with
+    // lr = training_mlr / 1000, BatchNorm in training mode, ++generation, back to eval mode.  Each mini-batch
+    // is one kb_trainer_forward_backward + kb_trainer_apply_sgd (tcgen05 forward / dgrad / wgrad).  Like the
+    // reference the batch arrays persist across mini-batches, so the last partial batch keeps the previous
+    // batch's rows (nn.cpp:278-298); the batches themselves are copied to the device as on the reference's CUDA
+    // path (its CPU path aliases one stack buffer for every stored batch, nn.cpp:300-316).
+    void train(int trajectories, float* inputs, float* obs_p, float* obs_v, bool detect_anomaly = false) {
+        std::unique_lock<std::shared_mutex> g(mut);
+        const float lr = (float)options::getInt("training_mlr", 5) / 1000.0f;
+        const int epochs = options::getInt("training_epochs", 8);
+        const int tbatch = options::getInt("training_batchsize", 8);
+        const size_t osz = (size_t)width * height * features;
+        kb_trainer* tr = nullptr;
+        check(kb_trainer_create(&tr, filters, residuals, tbatch));
+        struct Guard {
+            kb_trainer* t;
+            ~Guard() { kb_trainer_destroy(t); }
+        } guard{tr};
+        check(kb_trainer_load_blob(tr, blob.data(), blob.size()));
+        std::vector<int> picker(trajectories);
+        for (int i = 0; i < trajectories; ++i) picker[i] = i;
+        auto rng = std::default_random_engine{};
+        std::vector<float> next_input(tbatch * osz, 0.0f), next_policy((size_t)tbatch * psize, 0.0f), next_value(tbatch, 0.0f);
+        float firstloss = 0.0f, lastloss = 0.0f;
+        for (int epoch = 0; epoch < epochs; ++epoch) {
+            std::shuffle(picker.begin(), picker.end(), rng);
+            float avgloss = 0.0f, epfirst = 0.0f, eplast = 0.0f;
+            int nbatches = 0;
+            for (size_t base = 0; base < picker.size();) {
+                int i = 0;
+                for (; i < tbatch && base + i < picker.size(); ++i) {
+                    const size_t src = (size_t)picker[base + i];
+                    std::copy(inputs + src * osz, inputs + (src + 1) * osz, next_input.begin() + i * osz);
+                    std::copy(obs_p + src * psize, obs_p + (src + 1) * psize, next_policy.begin() + (size_t)i * psize);
+                    next_value[i] = obs_v[src];
+                }
+                base += i;
+                if (detect_anomaly)
+                    for (float v : next_input)
+                        if (v != v) throw std::runtime_error("training input contains NaN");
+                float loss = 0.0f;
+                check(kb_trainer_forward_backward(tr, next_input.data(), next_policy.data(), next_value.data(), tbatch, &loss));
+                if (detect_anomaly && loss != loss) throw std::runtime_error("forward output contains NaN");
+                check(kb_trainer_apply_sgd(tr, lr, 1.0f));
+                avgloss += loss;
+                if (!nbatches) epfirst = loss;
+                eplast = loss;
+                ++nbatches;
+            }
+            avgloss /= (float)(nbatches ? nbatches : 1);
+            std::cout << "Epoch " << epoch + 1 << "/" << epochs << ": loss " << epfirst << " => " << eplast << ", " << nbatches << " batches" << std::endl;
+            if (!epoch) firstloss = avgloss;
+            lastloss = avgloss;
+        }
+        ++generation;
+        std::cout << "Generated model " << generation << ", average loss " << firstloss << " to " << lastloss << " over " << epochs << " epochs\n";
+        std::vector<float> b(blob.size());
+        check(kb_trainer_export_blob(tr, b.data(), b.size()));
+        check(kb_net_load_blob(net, b.data(), b.size()));
+        blob.swap(b);
     }
     // Checkpoint = "KB20" + filters + residuals + generation + fp32 blob.  (The reference writes a
     // torch archive, nn.cpp:189-222; archive interop is SURVEY.md 8(f) #3.)

@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     Env,
     MCTS,
     NN,
+    Trainer,
     TreePool,
     TreeCfg,
     Position,

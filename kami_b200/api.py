@@ -109,6 +109,17 @@ _SIGS = {
     "kb_net_forward_dev": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "kb_net_planes_bytes": (C.c_size_t, [C.c_int]),
     "kb_net_flops": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "kb_trainer_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int]),
+    "kb_trainer_destroy": (C.c_int, [_P]),
+    "kb_trainer_load_blob": (C.c_int, [_P, C.POINTER(C.c_float), C.c_size_t]),
+    "kb_trainer_export_blob": (C.c_int, [_P, C.POINTER(C.c_float), C.c_size_t]),
+    "kb_trainer_export_grads": (C.c_int, [_P, C.POINTER(C.c_float), C.c_size_t]),
+    "kb_trainer_grad_buffer": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "kb_trainer_forward_backward": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                                              C.POINTER(C.c_float)]),
+    "kb_trainer_forward_backward_dev": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "kb_trainer_apply_sgd": (C.c_int, [_P, C.c_float, C.c_float]),
+    "kb_trainer_debug_activation": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "kb_net_debug_activation": (C.c_int, [_P, C.c_int, C.c_int, _f32p, _i32p]),
     "kb_net_debug_timestamps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_longlong), C.c_int, _i32p]),
     "kb_tree_default_cfg": (C.c_int, [C.POINTER(TreeCfg)]),
@@ -300,6 +311,65 @@ def static_eval(positions):
 
 
 # ---- NN (kami/nn/nn.h) --------------------------------------------------------------------------
+class Trainer:
+    """One mini-batch of NN::train (kami/nn/nn.cpp:224-377) at a time: forward in training mode, loss,
+    backward, plain SGD.  Weights travel as the flat fp32 blob of NN.load_blob (reference module names)."""
+
+    def __init__(self, filters, residuals, max_batch):
+        self.L = lib()
+        self.filters, self.residuals = filters, residuals
+        self.h = _P()
+        _ck(self.L.kb_trainer_create(C.byref(self.h), filters, residuals, max_batch))
+        self.n = self.L.kb_net_blob_floats(filters, residuals)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.kb_trainer_destroy(self.h)
+            self.h = None
+
+    def load_blob(self, blob):
+        blob = np.ascontiguousarray(blob, np.float32)
+        _ck(self.L.kb_trainer_load_blob(self.h, _fp(blob), blob.size))
+
+    def export_blob(self):
+        out = np.zeros(self.n, np.float32)
+        _ck(self.L.kb_trainer_export_blob(self.h, _fp(out), out.size))
+        return out
+
+    def export_grads(self):
+        out = np.zeros(self.n, np.float32)
+        _ck(self.L.kb_trainer_export_grads(self.h, _fp(out), out.size))
+        return out
+
+    def grad_buffer(self):
+        """(device address, number of floats) of the flat gradient vector (for the NCCL all-reduce)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _ck(self.L.kb_trainer_grad_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def forward_backward(self, obs, obs_p, obs_v):
+        obs = np.ascontiguousarray(obs, np.float32)
+        obs_p = np.ascontiguousarray(obs_p, np.float32)
+        obs_v = np.ascontiguousarray(obs_v, np.float32)
+        loss = C.c_float()
+        _ck(self.L.kb_trainer_forward_backward(self.h, _fp(obs), _fp(obs_p), _fp(obs_v), len(obs_v), C.byref(loss)))
+        return loss.value
+
+    def forward_backward_dev(self, obs_dev, obs_p_dev, obs_v_dev, batch, want_loss=True):
+        loss = C.c_float()
+        _ck(self.L.kb_trainer_forward_backward_dev(self.h, obs_dev, obs_p_dev, obs_v_dev, batch, C.byref(loss) if want_loss else None))
+        return loss.value
+
+    def apply_sgd(self, lr, grad_scale=1.0):
+        _ck(self.L.kb_trainer_apply_sgd(self.h, float(lr), float(grad_scale)))
+
+    def debug_activation(self, layer, which, board):
+        out = np.zeros((256, 64), np.float32)
+        ch = C.c_int()
+        _ck(self.L.kb_trainer_debug_activation(self.h, layer, which, board, _fp(out), C.byref(ch)))
+        return out[:ch.value].copy()
+
+
 class NN:
     """kami::NN: NN(width, height, features, psize) with `filters` / `residuals` taken from the
     arguments instead of the global options map (nn.cpp:42-43)."""

@@ -88,7 +88,7 @@ int kb_dev_alloc(void** out, size_t bytes) {
     KB_REQUIRE_INIT();
     KB_ARG(out, "out");
     KB_CUDA(cudaMalloc(out, bytes ? bytes : 16));
-    KB_CUDA(cudaMemset(*out, 0, bytes ? bytes : 16));
+    KB_CUDA(cudaMemsetAsync(*out, 0, bytes ? bytes : 16, main_stream()));
     return KB_OK;
 }
 int kb_dev_free(void* ptr) {

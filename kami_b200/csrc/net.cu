@@ -339,8 +339,10 @@ __global__ void __launch_bounds__(256, 1) k_conv(const ConvParams P) {
                                     }
                                     *cp = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                                 }
-                                ptx::fence_proxy_async_smem();
                             }
+                            // every lane fences, also those without a pixel of their own: the lane that issues the bulk
+                            // store must have ordered the tile's generic-proxy writes before the async proxy itself
+                            ptx::fence_proxy_async_smem();
                             __syncwarp();
                             KB_EP(e_math);
                             if (lane == 0) {
@@ -681,12 +683,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_conv2(cons
                                 if (P.skip) {  // x = skip + relu(conv + bias): ReLU before the add, none after (nn.cpp:31)
                                     const uint4 s4 = *cp;
                                     const uint32_t sk[4] = {s4.x, s4.y, s4.z, s4.w};
+                                    const float floor_ = P.relu ? 0.0f : -INFINITY;  // relu == 0: plain conv + skip (training passes)
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
                                         const int i0 = 8 * c + 2 * k;
-                                        const float lo = fmaxf(__uint_as_float(v[g][i0]) + bf[i0], 0.0f) + __uint_as_float(sk[k] << 16);
-                                        const float hi = fmaxf(__uint_as_float(v[g][i0 + 1]) + bf[i0 + 1], 0.0f) + __uint_as_float(sk[k] & 0xffff0000u);
+                                        const float lo = fmaxf(__uint_as_float(v[g][i0]) + bf[i0], floor_) + __uint_as_float(sk[k] << 16);
+                                        const float hi = fmaxf(__uint_as_float(v[g][i0 + 1]) + bf[i0 + 1], floor_) + __uint_as_float(sk[k] & 0xffff0000u);
                                         w4[k] = ptx::pack_bf16x2(lo, hi);
+                                    }
+                                } else if (!P.relu) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const int i0 = 8 * c + 2 * k;
+                                        w4[k] = ptx::pack_bf16x2(__uint_as_float(v[g][i0]) + bf[i0], __uint_as_float(v[g][i0 + 1]) + bf[i0 + 1]);
                                     }
                                 } else {
 #pragma unroll
@@ -698,9 +707,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_conv2(cons
                                 *cp = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                             }
                         }
-                        ptx::fence_proxy_async_smem();
                     }
+                    // every lane fences, also those without a pixel of their own (pad rows): a mover lane must have
+                    // ordered the tile's generic-proxy writes before the async proxy itself (lanes 1-3 move row
+                    // segments 1-3 but own pixels of segment 0)
+                    ptx::fence_proxy_async_smem();
                     __syncwarp();
+                    ptx::fence_proxy_async_smem();
                     KB_EP(e_math);
                     if (mover) {
                         ptx::bulk_s2g(P.out + seg_u4, stg_s + lane * 1024, 1024);
@@ -1334,13 +1347,13 @@ int net_reserve(kb_net* net, int batch) {
     KB_CUDA(cudaMalloc(&net->H, act_bytes(batch, 2)));
     // pad pixels (and unused channel chunks) must read as zero forever; epilogues and encoders
     // only ever write the chunks of board pixels they own
-    KB_CUDA(cudaMemset(net->P, 0, act_bytes(batch, IN_SLABS)));
-    KB_CUDA(cudaMemset(net->X, 0, act_bytes(batch, fs)));
-    KB_CUDA(cudaMemset(net->Y, 0, act_bytes(batch, fs)));
-    KB_CUDA(cudaMemset(net->H, 0, act_bytes(batch, 2)));
+    KB_CUDA(cudaMemsetAsync(net->P, 0, act_bytes(batch, IN_SLABS), main_stream()));
+    KB_CUDA(cudaMemsetAsync(net->X, 0, act_bytes(batch, fs), main_stream()));
+    KB_CUDA(cudaMemsetAsync(net->Y, 0, act_bytes(batch, fs), main_stream()));
+    KB_CUDA(cudaMemsetAsync(net->H, 0, act_bytes(batch, 2), main_stream()));
     if (!net->nan_flag) {
         KB_CUDA(cudaMalloc(&net->nan_flag, sizeof(int)));
-        KB_CUDA(cudaMemset(net->nan_flag, 0, sizeof(int)));
+        KB_CUDA(cudaMemsetAsync(net->nan_flag, 0, sizeof(int), main_stream()));
     }
     net->cap_boards = batch;
     return KB_OK;
@@ -1415,7 +1428,7 @@ static int run_conv(const Layer& L, const uint4* in, uint4* out, const uint4* sk
         p.skew = skew;
     }
     p.ts = g_conv_ts ? g_conv_ts + 16 * (g_conv_ts_slot++ % 8) : nullptr;
-    if (L.n_tile == 128 && out && L.relu && use_pair_kernel()) return launch_conv2<128>(p, st);
+    if (L.n_tile == 128 && out && use_pair_kernel()) return launch_conv2<128>(p, st);
     if (L.n_tile == 64) return launch_conv<64>(p, st);
     if (L.n_tile == 128) return launch_conv<128>(p, st);
     if (L.n_tile == 80) return launch_conv<80>(p, st);
@@ -1746,6 +1759,8 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
             net->fused = true;
         }
     }
+    // the uploads above went through the legacy stream, which does not order with the (non-blocking) main stream
+    KB_CUDA(cudaDeviceSynchronize());
     net->loaded = true;
     return KB_OK;
 }
@@ -1835,7 +1850,7 @@ int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, in
     KB_ARG(net, "net");
     if (enable && !net->ts_dev) {
         KB_CUDA(cudaMalloc(&net->ts_dev, 128 * sizeof(long long)));
-        KB_CUDA(cudaMemset(net->ts_dev, 0, 128 * sizeof(long long)));
+        KB_CUDA(cudaMemsetAsync(net->ts_dev, 0, 128 * sizeof(long long), main_stream()));
     }
     kb::g_conv_ts = enable && !net->fused ? net->ts_dev : nullptr;  // per-layer kernels: MMA-thread wait counters
     if (!out) kb::g_conv_ts_slot = 0;
@@ -1863,3 +1878,5 @@ int kb_net_flops(kb_net* net, double* tower, double* heads) {
 }
 
 }  // extern "C"
+
+#include "train.inl"

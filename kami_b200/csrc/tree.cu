@@ -1360,15 +1360,15 @@ int kb_pool_create(kb_pool** out, int n_trees, int node_capacity, const kb_tree_
     KB_CUDA(cudaMalloc(&d.nodes, nn * sizeof(Node)));
     KB_CUDA(cudaMalloc(&d.meta, nn * sizeof(u32)));
     KB_CUDA(cudaMalloc(&d.ctl, (size_t)n_trees * sizeof(TreeCtl)));
-    KB_CUDA(cudaMemset(d.ctl, 0, (size_t)n_trees * sizeof(TreeCtl)));
+    KB_CUDA(cudaMemsetAsync(d.ctl, 0, (size_t)n_trees * sizeof(TreeCtl), main_stream()));
     KB_CUDA(cudaMalloc(&d.error, sizeof(int)));
-    KB_CUDA(cudaMemset(d.error, 0, sizeof(int)));
+    KB_CUDA(cudaMemsetAsync(d.error, 0, sizeof(int), main_stream()));
     KB_CUDA(cudaMalloc(&d.stats, sizeof(Stats)));
-    KB_CUDA(cudaMemset(d.stats, 0, sizeof(Stats)));
+    KB_CUDA(cudaMemsetAsync(d.stats, 0, sizeof(Stats), main_stream()));
     KB_CUDA(cudaMalloc(&d.traj, (size_t)n_trees * d.traj_cap * sizeof(TrajSample)));
     KB_CUDA(cudaMalloc(&d.replay, (size_t)d.replay_cap * sizeof(ReplaySample)));
     KB_CUDA(cudaMalloc(&d.replay_head, sizeof(unsigned long long)));
-    KB_CUDA(cudaMemset(d.replay_head, 0, sizeof(unsigned long long)));
+    KB_CUDA(cudaMemsetAsync(d.replay_head, 0, sizeof(unsigned long long), main_stream()));
     KB_CUDA(cudaMalloc(&p->obs_dev, sizeof(float) * KB_OBSIZE));
     KB_CUDA(cudaMalloc(&p->pol_dev, sizeof(float) * KB_PSIZE));
     KB_CUDA(cudaMalloc(&p->int_dev, sizeof(int) * 4));
@@ -1675,7 +1675,7 @@ int kb_pool_get_stats(kb_pool* p, kb_pool_stats* out) {
 int kb_pool_reset_stats(kb_pool* p) {
     KB_ARG(p, "pool");
     KB_CUDA(cudaStreamSynchronize(main_stream()));
-    KB_CUDA(cudaMemset(p->d.stats, 0, sizeof(Stats)));
+    KB_CUDA(cudaMemsetAsync(p->d.stats, 0, sizeof(Stats), main_stream()));
     p->launches = 0;
     return KB_OK;
 }
@@ -1685,7 +1685,7 @@ int kb_pool_debug_select_profile(kb_pool* p, int enable, long long* out, int cap
     KB_ARG(p, "pool");
     if (enable && !p->d.dbg) {
         KB_CUDA(cudaMalloc(&p->d.dbg, sizeof(long long) * 8 * (size_t)p->d.n_trees));
-        KB_CUDA(cudaMemset(p->d.dbg, 0, sizeof(long long) * 8 * (size_t)p->d.n_trees));
+        KB_CUDA(cudaMemsetAsync(p->d.dbg, 0, sizeof(long long) * 8 * (size_t)p->d.n_trees, main_stream()));
     }
     if (out && p->d.dbg) {
         KB_CUDA(cudaStreamSynchronize(main_stream()));

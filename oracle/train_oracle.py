@@ -25,6 +25,25 @@ import nn_oracle as NO
 BN_MOMENTUM = 0.1
 
 
+def _id(x):
+    return x
+
+
+def _bf16(x):
+    """Round a tensor to bf16 where the CUDA path stores it as bf16 (straight-through for autograd) and
+    round the gradient that flows back into it as well (activation gradients are bf16 tensors there)."""
+    y = x.detach().to(torch.bfloat16).to(torch.float32)
+    out = x + (y - x).detach()
+    if out.requires_grad:
+        out.register_hook(lambda g: g.to(torch.bfloat16).to(torch.float32))
+    return out
+
+
+def _bf16_w(w):
+    """bf16 operand copy of an fp32 master weight (gradient passes straight through to the master)."""
+    return w + (w.detach().to(torch.bfloat16).to(torch.float32) - w).detach()
+
+
 def _bn(x, p, name, new_stats):
     """BatchNorm2d in training mode on NCHW x; records the updated running statistics."""
     w, b = p[name + ".weight"], p[name + ".bias"]
@@ -40,18 +59,32 @@ def _bn(x, p, name, new_stats):
     return y
 
 
-def forward_train(p, obs, filters, residuals, new_stats):
-    """nn.cpp:59-91 with BatchNorm in training mode.  obs [B,64,30] (NHWC as Env::observe writes it)."""
+def forward_train(p, obs, filters, residuals, new_stats, emulate_bf16=False, capture=None):
+    """nn.cpp:59-91 with BatchNorm in training mode.  obs [B,64,30] (NHWC as Env::observe writes it).
+    emulate_bf16: round conv weights, activations and activation gradients to bf16 at the points where
+    the CUDA training step stores bf16 (a sharp check of the kernels; fp32 is the reference arithmetic)."""
+    ra, rw = (_bf16, _bf16_w) if emulate_bf16 else (_id, _id)
     B = obs.shape[0]
     x = obs.reshape(B, 8, 8, NO.NFEATURES).permute(0, 3, 1, 2)
-    x = torch.relu(_bn(Fn.conv2d(x, p["conv1.weight"], p["conv1.bias"], padding=1), p, "batchnorm1", new_stats))
+
+    def block(x, conv, bn, pad, skip=None):
+        pre = ra(Fn.conv2d(x, rw(p[conv + ".weight"]), p[conv + ".bias"], padding=pad))
+        y = torch.relu(_bn(pre, p, bn, new_stats))
+        out = ra(y if skip is None else skip + y)
+        if capture is not None:  # [B, C, 64] like kb_trainer_debug_activation
+            capture.append((conv, pre.detach().flatten(2).numpy().copy(), out.detach().flatten(2).numpy().copy()))
+        return out
+
+    x = block(x, "conv1", "batchnorm1", 1)
     for i in range(residuals):
         r = "residual%d" % i
         skip = x
-        x = torch.relu(_bn(Fn.conv2d(x, p[r + ".conv1.weight"], p[r + ".conv1.bias"], padding=1), p, r + ".batchnorm1", new_stats))
-        x = skip + torch.relu(_bn(Fn.conv2d(x, p[r + ".conv2.weight"], p[r + ".conv2.bias"], padding=1), p, r + ".batchnorm2", new_stats))
-    ph = torch.relu(_bn(Fn.conv2d(x, p["policyconv.weight"], p["policyconv.bias"]), p, "pbatchnorm", new_stats))
-    ph = Fn.conv2d(ph, p["policyconv2.weight"], p["policyconv2.bias"])
+        x = block(x, r + ".conv1", r + ".batchnorm1", 1)
+        x = block(x, r + ".conv2", r + ".batchnorm2", 1, skip)
+    ph = block(x, "policyconv", "pbatchnorm", 0)
+    ph = Fn.conv2d(ph, rw(p["policyconv2.weight"]), p["policyconv2.bias"])
+    if emulate_bf16 and ph.requires_grad:
+        ph.register_hook(lambda g: g.to(torch.bfloat16).to(torch.float32))  # dlogits are stored as bf16
     ph = ph.permute(0, 2, 3, 1).flatten(1)
     ph = torch.exp(torch.log_softmax(ph, 1))
     vh = torch.relu(_bn(Fn.conv2d(x, p["valueconv.weight"], p["valueconv.bias"]), p, "vbatchnorm", new_stats))
@@ -69,12 +102,12 @@ def trainable(name):
     return not (name.endswith("running_mean") or name.endswith("running_var"))
 
 
-def train_step(params, obs, obs_p, obs_v, filters, residuals, lr):
+def train_step(params, obs, obs_p, obs_v, filters, residuals, lr, emulate_bf16=False, capture=None):
     """One mini-batch of NN::train.  params: dict name -> numpy fp32 (nn_oracle.param_order).
     Returns (new params dict, loss, grads dict)."""
     p = {k: torch.tensor(np.asarray(v, np.float32), requires_grad=trainable(k)) for k, v in params.items()}
     new_stats = {}
-    ph, vh = forward_train(p, torch.tensor(np.asarray(obs, np.float32)), filters, residuals, new_stats)
+    ph, vh = forward_train(p, torch.tensor(np.asarray(obs, np.float32)), filters, residuals, new_stats, emulate_bf16, capture)
     loss = loss_fn(ph, vh, torch.tensor(np.asarray(obs_p, np.float32)), torch.tensor(np.asarray(obs_v, np.float32)))
     loss.backward()
     out, grads = {}, {}

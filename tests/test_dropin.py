@@ -11,7 +11,7 @@ import pytest
 import harness as H
 
 DROPIN = os.path.join(H.ROOT, "kami", "_dropin")
-TESTS = ["encoding", "mcts", "bench", "nn", "nncuda", "selfplay", "play", "nndisk"]
+TESTS = ["encoding", "mcts", "bench", "nn", "nncuda", "selfplay", "play", "nndisk", "nntrain"]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/test"), reason="reference sources not present")
@@ -52,3 +52,22 @@ def test_reference_nn_and_mcts_programs_run(kb):
     except subprocess.TimeoutExpired as e:
         text = (e.stdout or b"").decode()
     assert "Observations / second" in text
+
+
+@pytest.mark.gpu
+def test_reference_nntrain_program_runs(kb):
+    """test/nntrain.cpp, unmodified: NN::train on 512 random samples (8 epochs of 64 mini-batches of 8, options
+    defaults: 256 filters, 2 residual blocks) through the CUDA training step.  The data is pure noise (5 % of the
+    4672 policy targets set to 1, uniform inputs), so the loss only has to stay finite and near its start."""
+    import re
+
+    exe = os.path.join(DROPIN, "test_nntrain")
+    if not os.path.exists(exe):
+        pytest.skip("kami/_dropin not built")
+    out = subprocess.run([exe], capture_output=True, timeout=300)
+    assert out.returncode == 0, out.stderr.decode()[-400:]
+    text = out.stdout.decode()
+    ep = re.findall(r"Epoch (\d+)/8: loss ([-+.e\d]+) => ([-+.e\d]+), 64 batches", text)
+    assert len(ep) == 8 and "Generated model 1" in text, text[-600:]
+    first = float(ep[0][1])
+    assert all(0.5 * first < float(a) < 1.05 * first and 0.5 * first < float(b) < 1.05 * first for _, a, b in ep)
