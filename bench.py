@@ -259,13 +259,98 @@ def workload_config():
             "l2": "inputs larger than L2: live node pools ~0.6 MB x 1024 trees per GPU >> 126 MB, no flush"}
 
 
+def random_blob(F, R, seed):
+    """Random-init weights in kb_net_load_blob order with LibTorch's default distributions (U(+-1/sqrt(fan_in)) for
+    conv / linear weights and biases; BatchNorm gamma 1, beta 0, running mean 0, running var 1), numpy only."""
+    rng = np.random.RandomState(seed)
+    parts = []
+
+    def conv(o, c, k):
+        b = 1.0 / np.sqrt(c * k * k)
+        parts.append(rng.uniform(-b, b, o * c * k * k))
+        parts.append(rng.uniform(-b, b, o))
+
+    def bn(c):
+        parts.extend([np.ones(c), np.zeros(c), np.zeros(c), np.ones(c)])
+
+    conv(F, 30, 3)
+    bn(F)
+    for _ in range(R):
+        conv(F, F, 3)
+        bn(F)
+        conv(F, F, 3)
+        bn(F)
+    conv(128, F, 1)
+    bn(128)
+    conv(73, 128, 1)
+    conv(1, F, 1)
+    bn(1)
+    parts.append(rng.uniform(-0.125, 0.125, 256 * 64))
+    parts.append(rng.uniform(-0.125, 0.125, 256))
+    return np.concatenate(parts).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# training leg (SURVEY 8(f) #1, BASELINE config 5)
+# ---------------------------------------------------------------------------------------------
+def train_leg(api, L, dist, local, world, pool, F=256, R=20, B=1024, steps=5):
+    """Synthetic replay batch from the product's own path: the pool's current leaf positions (1024 distinct
+    mid-game positions), their input planes (kb_encode_planes) and a random sparse visit distribution over
+    their legal actions (kb_legal_actions) -- the shape of ReplayBuffer::select_batch (replaybuffer.h:61-84)."""
+    import kami_b200
+    from kami_b200.parallel import data_parallel_step
+
+    rank = dist.get_rank() if dist is not None else 0
+    pool.select()
+    pos = pool.leaf_positions()[:B]
+    obs = api.encode_planes(pos)
+    acts, cnt = api.legal_actions(pos)
+    rng = np.random.RandomState(17 + rank)
+    pi = np.zeros((len(pos), 4672), np.float32)
+    for i in range(len(pos)):
+        w = rng.randint(1, 40, size=int(cnt[i])).astype(np.float32)
+        pi[i, acts[i, :cnt[i]]] = w / w.sum()
+    z = rng.choice(np.array([-1.0, 0.5, 1.0], np.float32), size=len(pos)).astype(np.float32)
+    rep = (B + len(pos) - 1) // len(pos)
+    arrs = [np.ascontiguousarray(np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:B], np.float32) for a in (obs, pi, z)]
+    tr = kami_b200.Trainer(F, R, B)
+    tr.load_blob(random_blob(F, R, seed=1 + 0 * rank))  # every replica starts from the same weights
+    devp = []
+    for a in arrs:
+        p = C.c_void_p()
+        api._ck(L.kb_dev_alloc(C.byref(p), a.nbytes))
+        api._ck(L.kb_dev_upload(p, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        devp.append(p)
+    view = None
+    for _ in range(3):
+        view = data_parallel_step(tr, dist, "cuda:%d" % local, L, devp[0], devp[1], devp[2], B, 0.002, view)
+    ms = C.c_float()
+    barrier(dist, local)
+    L.kb_dev_sync()
+    L.kb_timer_start()
+    for _ in range(steps):
+        view = data_parallel_step(tr, dist, "cuda:%d" % local, L, devp[0], devp[1], devp[2], B, 0.002, view)
+    L.kb_timer_stop(C.byref(ms))
+    barrier(dist, local)
+    t = reduce_max(dist, local, ms.value) / steps
+    loss = tr.forward_backward_dev(devp[0], devp[1], devp[2], B)
+    for p in devp:
+        L.kb_dev_free(p)
+    tower_f = 2.0 * 64 * (9 * 30) * F + R * 2.0 * (2.0 * 64 * 9 * F * F)
+    heads_f = 2.0 * 64 * F * 128 + 2.0 * 64 * 128 * 73
+    hbm, tfp, tfs, kind = peaks()
+    tfl = 3.0 * (tower_f + heads_f) * B * world / (t * 1e-3) / 1e12
+    return {"batch_per_gpu": B, "n_gpus": world, "ms_per_step": t, "samples_per_sec": B * world / (t * 1e-3),
+            "tflops_3x_forward_convention": tfl, "frac_of_bf16_peak_per_gpu": tfl / world / tfp,
+            "grad_bucket_mb": tr.n * 4 / 1e6, "collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce(sum), one fp32 bucket per step",
+            "loss_after": loss, "peak_kind": kind}
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local, dist):
-    import harness as H
     import kami_b200
-    import nn_oracle as NO
     from kami_b200 import api
     from kami_b200.parallel import per_rank_seed
 
@@ -274,9 +359,9 @@ def run_ours(args, rank, world, local, dist):
     hbm_peak, tf_peak, tf_sustained, peak_kind = peaks()
 
     net = kami_b200.NN(FILTERS, RESIDUALS)
-    net.load_blob(NO.pack_blob(NO.init_params(FILTERS, RESIDUALS, seed=1), FILTERS, RESIDUALS))
+    net.load_blob(random_blob(FILTERS, RESIDUALS, seed=1))
     kw = dict(noise_weight=0.05, selfplay_nodes=SELFPLAY_NODES, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5,
-              alpha_cutoff=20, draw_value_pct=50, **H.DEF_YML)
+              alpha_cutoff=20, draw_value_pct=50, **kami_b200.DEF_YML)
     pool = kami_b200.TreePool(TREES_PER_GPU, NODE_CAPACITY, api.tree_cfg(seed=per_rank_seed(1000, rank), **kw))
 
     def timed_steps(fn, k):
@@ -308,25 +393,24 @@ def run_ours(args, rank, world, local, dist):
     # roofline of the dominant kernel of the step (timed live with CUDA events inside kb_pool_step)
     t_f, h_f = net.flops()
     phases = {"select+encode": ph["select"], "tower+heads": ph["tower"], "expand+backup": ph["expand"]}
-    dominant = max(phases, key=phases.get)
-    if dominant == "tower+heads":
-        achieved = (t_f + h_f) * TREES_PER_GPU / (ph["tower"] * 1e-3) / 1e12
-        roof = {"kernel": "k_tower64 (one fused tcgen05 launch: %dx%d tower + policy/value heads + softmax)" % (RESIDUALS, FILTERS),
-                "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one k_tower64 launch at 1024 boards, from the
-                # ncu --set full capture summarised in profiles/r01_ncu_summary_v2.txt (12.607 MB read: 147 input
-                # slabs of 80 KB + weights; the 19 MB policy rows stay in L2 for k_pool_expand)
-                "traffic": TOWER64_DRAM_BYTES_PER_LAUNCH if TREES_PER_GPU == 1024 else None,
-                "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst",
-                "algorithmic": "%.3f MFLOP/position x %d positions per launch group" % ((t_f + h_f) / 1e6, TREES_PER_GPU)}
-    else:
-        per_step = (12.0 * st["children_scanned"] + 16.0 * st["path_nodes"] + 16.0 * st["children_created"]) / max(1, args.steps)
-        per_step += 3904.0 * TREES_PER_GPU
-        dur = (ph["select"] + ph["expand"]) * 1e-3
-        achieved = per_step / dur / 1e9
-        roof = {"kernel": "k_pool_select + k_pool_expand", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                "algorithmic": "12 B x children scanned + 16 B x path nodes + 16 B x children created + 3904 B planes per leaf"}
+    # dominant kernel of the step: k_tower64 (56 % of the step in the ncu launch list, profiles/r01_ncu_summary_v2.txt)
+    achieved = (t_f + h_f) * TREES_PER_GPU / (ph["tower"] * 1e-3) / 1e12
+    roof = {"kernel": "k_tower64 (one fused tcgen05 launch: %dx%d tower + policy/value heads + legal-move softmax)" % (RESIDUALS, FILTERS),
+            "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one k_tower64 launch at 1024 boards, from the
+            # ncu --set full capture summarised in profiles/r01_ncu_summary_v2.txt (12.607 MB read: 147 input
+            # slabs of 80 KB + weights)
+            "traffic": TOWER64_DRAM_BYTES_PER_LAUNCH if TREES_PER_GPU == 1024 else None,
+            "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst",
+            "algorithmic": "%.3f MFLOP/position x %d positions per launch" % ((t_f + h_f) / 1e6, TREES_PER_GPU)}
+    # the tree kernels (latency-bound, one warp per tree): algorithmic bytes counted by the kernels themselves
+    per_step = (12.0 * st["children_scanned"] + 16.0 * st["path_nodes"] + 16.0 * st["children_created"]) / max(1, args.steps)
+    per_step += 3904.0 * TREES_PER_GPU
+    dur = (ph["select"] + ph["expand"]) * 1e-3
+    roof_tree = {"kernel": "k_pool_select + k_pool_expand", "bound": "hbm", "achieved": per_step / dur / 1e9, "peak": hbm_peak,
+                 "unit": "GB/s", "frac": per_step / dur / 1e9 / hbm_peak, "traffic": 2369024 + 13312 + 2436864,
+                 "traffic_unit": "bytes/step (ncu, select + expand)", "peak_kind": peak_kind,
+                 "algorithmic": "12 B x children scanned + 16 B x path nodes + 16 B x children created + 3904 B planes per leaf"}
 
     # end to end through the reference-shaped host-buffer API (pinned host memory)
     n = TREES_PER_GPU
@@ -355,7 +439,7 @@ def run_ours(args, rank, world, local, dist):
         # 20x256 tower (BASELINE config 5's network) forward only: % of dense BF16 peak at batch 1024
         try:
             big = kami_b200.NN(256, 20)
-            big.load_blob(NO.pack_blob(NO.init_params(256, 20, seed=1), 256, 20))
+            big.load_blob(random_blob(256, 20, seed=1))
             B = 1024
             planes, pol, val = C.c_void_p(), C.c_void_p(), C.c_void_p()
             api._ck(L.kb_dev_alloc(C.byref(planes), L.kb_net_planes_bytes(B)))
@@ -387,6 +471,16 @@ def run_ours(args, rank, world, local, dist):
                    "sample": "%.0f s of 3 inference threads x 16 trees (options.def.yml) on %d host cores, %s" % (
                        dt, cores, "unmodified reference Env/MCTS + LibTorch CPU fp32 NN" if kind == "reference" else "oracle port")}
 
+    if not args.no_extras:
+        # BASELINE config 5: data-parallel NN::train mini-batches of the 20x256 tower, bf16 tcgen05 forward /
+        # dgrad / wgrad, ONE NCCL all-reduce of the flat fp32 gradient bucket (95 MB) per step over NVLink
+        try:
+            tt = train_leg(api, L, dist, local, world, pool)
+            if rank == 0:
+                extras["train_20x256"] = tt
+        except Exception as e:
+            if rank == 0:
+                extras["train_20x256"] = {"error": str(e)}
     for p in bufs:
         L.kb_host_free_pinned(p)
     if rank != 0:
@@ -396,8 +490,9 @@ def run_ours(args, rank, world, local, dist):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(),
         "positions_per_sec": moves / (ms * 1e-3),
-        "phase_ms_last_step": phases,
+        "phase_ms_mean_of_32_sampled_steps": phases,
         "roofline": roof,
+        "roofline_tree_kernels": roof_tree,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps},
         "gpu_launches": int(st["kernel_launches"]),

@@ -1282,6 +1282,8 @@ struct kb_pool {
     unsigned selects_since_compact;
     int policy_mode;  // kb_pool_step: 0 softmax over the legal moves only (default), 1 dense [n][4672] softmax
     cudaEvent_t ev[6];
+    cudaEvent_t evs[32][4];  // phase boundaries of up to 32 evenly spaced iterations of a kb_pool_step call
+    bool evs_ready;
     kb_phase_ms last;
     unsigned long long replay_tail;
 };
@@ -1399,6 +1401,9 @@ int kb_pool_destroy(kb_pool* p) {
     cudaFree(p->child_i); cudaFree(p->child_f); cudaFree(p->leaf_dev); cudaFree(p->policy_dev); cudaFree(p->value_dev);
     cudaFree(p->obs_batch_dev); cudaFree(d.dbg);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(p->ev[i]);
+    if (p->evs_ready)
+        for (int i = 0; i < 32; ++i)
+            for (int j = 0; j < 4; ++j) cudaEventDestroy(p->evs[i][j]);
     delete p;
     return KB_OK;
 }
@@ -1593,29 +1598,45 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters) {
     cudaStream_t st = main_stream();
     uint4* planes = reinterpret_cast<uint4*>(net_input_planes(net));
     const bool legal = p->policy_mode == 0;
+    if (!p->evs_ready) {
+        for (int i = 0; i < 32; ++i)
+            for (int j = 0; j < 4; ++j) KB_CUDA(cudaEventCreate(&p->evs[i][j]));
+        p->evs_ready = true;
+    }
+    // phase times are averaged over up to 32 evenly spaced iterations: single steps vary a lot (a tree that
+    // absorbs many terminal visits stretches its select)
+    const int nsamp = iters < 32 ? iters : 32, stride = iters / nsamp;
     KB_CUDA(cudaEventRecord(p->ev[0], st));
     for (int it = 0; it < iters; ++it) {
-        const bool timed = it == iters - 1;
-        if (timed) KB_CUDA(cudaEventRecord(p->ev[1], st));
+        const int k = it / stride;
+        const bool timed = it % stride == 0 && k < nsamp;
+        if (timed) KB_CUDA(cudaEventRecord(p->evs[k][0], st));
         if ((r = pool_launch_select(p, planes, nullptr, st))) return r;
-        if (timed) KB_CUDA(cudaEventRecord(p->ev[2], st));
+        if (timed) KB_CUDA(cudaEventRecord(p->evs[k][1], st));
         if (legal)  // softmax over the legal moves only: priors straight into p->policy_dev[tree][128]
             r = net_forward_legal_async(net, planes, n, &p->d.ctl[0].leaf_act[0], &p->d.ctl[0].leaf_nact, sizeof(TreeCtl), p->policy_dev, p->value_dev, st);
         else
             r = net_forward_async(net, planes, n, p->policy_dev, p->value_dev, st);
         if (r) return r;
-        if (timed) KB_CUDA(cudaEventRecord(p->ev[3], st));
+        if (timed) KB_CUDA(cudaEventRecord(p->evs[k][2], st));
         k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 1, 0, legal ? 1 : 0);
         KB_CUDA(cudaGetLastError());
-        if (timed) KB_CUDA(cudaEventRecord(p->ev[4], st));
+        if (timed) KB_CUDA(cudaEventRecord(p->evs[k][3], st));
         p->launches += 2 + (unsigned long long)net_launches_per_forward(net);
     }
     KB_CUDA(cudaEventRecord(p->ev[5], st));
     r = pool_check(p, true);
     if (r) return r;
-    cudaEventElapsedTime(&p->last.select, p->ev[1], p->ev[2]);
-    cudaEventElapsedTime(&p->last.tower, p->ev[2], p->ev[3]);
-    cudaEventElapsedTime(&p->last.expand, p->ev[3], p->ev[4]);
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < nsamp; ++k)
+        for (int j = 0; j < 3; ++j) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, p->evs[k][j], p->evs[k][j + 1]);
+            acc[j] += ms;
+        }
+    p->last.select = acc[0] / nsamp;
+    p->last.tower = acc[1] / nsamp;
+    p->last.expand = acc[2] / nsamp;
     cudaEventElapsedTime(&p->last.total, p->ev[0], p->ev[5]);
     p->last.encode = 0.0f;  // fused into select
     p->last.heads = 0.0f;   // reported inside tower

@@ -1,4 +1,8 @@
-"""Multi-GPU plumbing of the self-play path: games never interact (selfplay.cpp:97-200), so the
+"""Multi-GPU plumbing.  Training (BASELINE config 5): data-parallel over replay batches -- every rank
+runs kb_trainer_forward_backward on its own mini-batch, the flat fp32 gradient vector is all-reduced over
+NCCL / NVLink as ONE bucket (sum), and every replica applies the identical SGD step scaled by 1 / world.
+
+Self-play path: games never interact (selfplay.cpp:97-200), so the
 path shards by game with NO data-path collective.  torch.distributed is used only to launch one
 process per GPU, to barrier around the timed region and to combine per-rank counters / device
 times (max over ranks).  Backend-agnostic so the CPU tests can run it on gloo."""
@@ -51,3 +55,48 @@ def whole_job_throughput(reducer, local_units, local_ms):
     units = reducer.sum(local_units)
     ms = reducer.max(local_ms)
     return units / (ms * 1e-3), units, ms
+
+
+# ---- data-parallel training: the one collective of the system ------------------------------------------
+class _DevArray:
+    """A raw device pointer dressed as a CUDA array so torch can view it without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+def gradient_tensor(trainer, device):
+    """torch fp32 view (no copy) of the trainer's flat gradient vector on `device`."""
+    import torch
+
+    ptr, n = trainer.grad_buffer()
+    return torch.as_tensor(_DevArray(ptr, n), device=device)
+
+
+def average_host_gradients(dist, grads):
+    """The same reduction on a host array (gloo) -- what the CPU test of the N > 1 logic runs."""
+    import torch
+
+    t = torch.from_numpy(grads)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t /= dist.get_world_size()
+    return t.numpy()
+
+
+def data_parallel_step(trainer, dist, device, lib, obs_dev, pi_dev, z_dev, batch, lr, grad_view=None):
+    """One data-parallel training step: local forward/backward, NCCL all-reduce(sum) of the gradient bucket,
+    SGD with the 1/world scale.  The library runs on its own stream, torch's NCCL on torch's: both sides are
+    synchronised around the collective.  Returns the gradient view for reuse."""
+    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+    trainer.forward_backward_dev(obs_dev, pi_dev, z_dev, batch, want_loss=False)
+    if world > 1:
+        import torch
+
+        if grad_view is None:
+            grad_view = gradient_tensor(trainer, device)
+        lib.kb_dev_sync()
+        dist.all_reduce(grad_view, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+    trainer.apply_sgd(lr, 1.0 / world)
+    return grad_view
