@@ -145,6 +145,8 @@ int kb_tree_reset(kb_pool* p, int tree);                           /* :331-339 *
 int kb_tree_snapshot(kb_pool* p, int tree, float* pspace);         /* :341-348 */
 int kb_tree_root_children(kb_pool* p, int tree, int32_t* action, int32_t* n, float* w, float* prior, int cap, int* count);
 int kb_tree_root_w(kb_pool* p, int tree, float* w);
+/* actions from the root to the pending leaf: the reference's Env sits AT the leaf after select() (mcts.h:252-254) */
+int kb_tree_leaf_path(kb_pool* p, int tree, int32_t* actions, int cap, int* depth);
 int kb_tree_digest(kb_pool* p, int tree, uint64_t* digest, int64_t* count);
 int kb_tree_env(kb_pool* p, int tree, kb_position* out);           /* MCTS::get_env() root position */
 

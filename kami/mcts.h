@@ -111,7 +111,28 @@ class MCTS {
 
     int n() { return root->n; }
 
+   private:
+    // The reference's select() leaves its Env AT the leaf until expand() unwinds it (mcts.h:252-254, 320-326) and
+    // callers look at it there (evaluate.cpp:80-90 reads get_env().turn()).  The device tree keeps its own
+    // positions; this host mirror follows only when somebody asks (get_env() while a leaf is pending).
+    bool pending = false;
+    int mirrored_plies = 0;
+    void mirror_to_leaf() {
+        if (!pending || mirrored_plies) return;
+        int32_t path[255];
+        int depth = 0;
+        kb_check(kb_tree_leaf_path(pool, slot, path, 255, &depth));
+        for (int i = 0; i < depth; ++i) env.push(path[i]);
+        mirrored_plies = depth;
+    }
+    void mirror_to_root() {
+        for (; mirrored_plies > 0; --mirrored_plies) env.pop();
+        pending = false;
+    }
+
+   public:
     void push(int action) {
+        mirror_to_root();
         int rc = kb_tree_push(pool, slot, action);
         if (rc == KB_ERR_NO_CHILD) throw std::runtime_error("no child for action");
         kb_check(rc);
@@ -129,14 +150,21 @@ class MCTS {
         int need = 0;
         kb_check(kb_tree_select(pool, slot, obs, &need));
         if (!need) refresh_root();  // a terminal leaf was backed up
+        pending = need != 0;
         return need != 0;
     }
     void expand(float* policy, float value, bool disable_bootstrap = false) {
+        mirror_to_root();
         kb_check(kb_tree_expand(pool, slot, policy, value, disable_bootstrap ? 1 : 0));
         refresh_root();
     }
-    Env& get_env() { return env; }
+    Env& get_env() {
+        mirror_to_leaf();
+        return env;
+    }
     void reset() {
+        mirrored_plies = 0;
+        pending = false;
         kb_check(kb_tree_reset(pool, slot));
         env = Env();
         refresh_root();

@@ -135,6 +135,7 @@ _SIGS = {
     "kb_tree_snapshot": (C.c_int, [_P, C.c_int, _f32p]),
     "kb_tree_root_children": (C.c_int, [_P, C.c_int, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p]),
     "kb_tree_root_w": (C.c_int, [_P, C.c_int, _f32p]),
+    "kb_tree_leaf_path": (C.c_int, [_P, C.c_int, _i32p, C.c_int, _i32p]),
     "kb_tree_digest": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
     "kb_tree_env": (C.c_int, [_P, C.c_int, _P]),
     "kb_pool_select": (C.c_int, [_P]),
@@ -542,6 +543,13 @@ class MCTS:
         a = C.c_int32()
         _ck(self.L.kb_tree_pick(self.ph, self.i, float(alpha), float(u01), C.byref(a)))
         return a.value
+
+    def leaf_path(self):
+        """Actions from the root to the leaf waiting for the network (empty when none is pending)."""
+        a = np.zeros(255, np.int32)
+        d = C.c_int32()
+        _ck(self.L.kb_tree_leaf_path(self.ph, self.i, _ip(a), 255, C.byref(d)))
+        return a[:d.value].copy()
 
     def push(self, action):
         _ck(self.L.kb_tree_push(self.ph, self.i, int(action)))

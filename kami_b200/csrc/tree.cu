@@ -793,6 +793,14 @@ __global__ void k_tree_pick(PoolDev P, int t, float alpha, double u01, int* out)
 }
 __global__ void k_tree_push(PoolDev P, int t, int action) { push_once(P, t, action); }
 __global__ void k_tree_reset(PoolDev P, int t) { tree_reset(P, t); }
+// actions along the selected path (root -> pending leaf); out[0] = depth (0 when no leaf is pending)
+__global__ void k_tree_leaf_path(PoolDev P, int t, int* out, int cap) {
+    const TreeCtl& c = P.ctl[t];
+    const u32* meta = tree_meta(P, t, c.space);
+    const int depth = c.state == 1 ? c.depth : 0;
+    if (threadIdx.x == 0) out[0] = depth;
+    for (int d = threadIdx.x; d < depth && d + 1 < cap; d += 32) out[1 + d] = (int)(meta[c.path[d + 1]] & 0xFFFF);
+}
 __global__ void k_tree_snapshot(PoolDev P, int t, float* ps) {  // mcts.h:341-348
     const TreeCtl& c = P.ctl[t];
     const Node* nodes = tree_nodes(P, t, c.space);
@@ -1423,6 +1431,26 @@ int kb_tree_n(kb_pool* p, int tree, int* n) {
     KB_CUDA(cudaStreamSynchronize(main_stream()));
     p->launches++;
     *n = info.n;
+    return KB_OK;
+}
+// The moves from the root to the leaf that waits for the network (MCTS::select leaves the reference's Env AT that
+// leaf, mcts.h:252-254; callers such as evaluate.cpp:80-90 read get_env().turn() there).
+int kb_tree_leaf_path(kb_pool* p, int tree, int32_t* actions, int cap, int* depth) {
+    KB_TREE_ARGS();
+    KB_ARG(actions && depth && cap > 0, "actions/cap/depth");
+    const int n = cap < 255 ? cap : 255;
+    k_tree_leaf_path<<<1, 32, 0, main_stream()>>>(p->d, tree, p->child_i, n + 1);
+    KB_CUDA(cudaGetLastError());
+    int host[256];
+    KB_CUDA(cudaMemcpyAsync(host, p->child_i, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, main_stream()));
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
+    p->launches++;
+    *depth = host[0];
+    if (host[0] > n) {
+        set_error("leaf path (%d plies) does not fit the caller's buffer (%d)", host[0], n);
+        return KB_ERR_CAPACITY;
+    }
+    for (int i = 0; i < host[0]; ++i) actions[i] = host[1 + i];
     return KB_OK;
 }
 int kb_tree_select(kb_pool* p, int tree, float* obs, int* need_eval) {

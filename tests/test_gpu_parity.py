@@ -164,6 +164,35 @@ def test_mcts_vs_oracle_with_compaction(kb):
             break
 
 
+def test_leaf_path_replays_to_the_leaf_position(kb):
+    """kb_tree_leaf_path: the reference's Env sits at the leaf after select() (mcts.h:252-254); replaying the
+    returned actions from the root reaches the leaf whose planes select() returned."""
+    cfg = dict(noise_weight=0.0, **H.DEF_YML)
+    t = kb.MCTS(cfg=_cfg(kb, **cfg))
+    o = H.OracleMcts(H.default_cfg(**cfg))
+    rng = np.random.RandomState(2)
+    deepest = 0
+    for it in range(60):
+        so, oo = o.select()
+        sd, od = t.select()
+        assert so == sd
+        if not so:
+            continue
+        path = t.leaf_path()
+        deepest = max(deepest, len(path))
+        e = H.OracleEnv()
+        for a in path:
+            e.push(int(a))
+        assert np.array_equal(e.observe(), od) and np.array_equal(e.export(), o.env.export())
+        p = rng.rand(H.PSIZE).astype(np.float32)
+        p /= p.sum()
+        v = float(np.float32(rng.rand() * 2 - 1))
+        o.expand(p, v)
+        t.expand(p, v)
+        assert len(t.leaf_path()) == 0
+    assert deepest >= 2
+
+
 def test_mcts_errors(kb):
     from kami_b200 import KamiError
 
