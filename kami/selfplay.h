@@ -1,9 +1,11 @@
 // kami::Selfplay over the B200 C ABI -- the surface of the reference's kami/selfplay.h:24-102.
 // Each inference thread owns a device-resident pool of `selfplay_batch` trees and runs the whole
 // loop of Selfplay::inference_main (selfplay.cpp:113-200) on the GPU with kb_pool_step; finished
-// games are drained into the host ReplayBuffer.  Training threads (train + arena) are
-// SURVEY.md 8(f) items and are not started.
+// games are drained into the host ReplayBuffer.  Training threads follow Selfplay::training_main
+// (selfplay.cpp:215-304): wait for the replay target, clone the model, ReplayBuffer::select_batch, NN::train
+// (the CUDA training step), kami::eval (the arena), and on acceptance write + read the model file.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <iostream>
@@ -15,6 +17,7 @@
 #include <vector>
 
 #include "env.h"
+#include "evaluate.h"
 #include "nn/nn.h"
 #include "options.h"
 #include "replaybuffer.h"
@@ -33,14 +36,16 @@ class Selfplay {
             partial_trajectories.emplace_back(0);
             inference.push_back(std::thread(&Selfplay::inference_main, this, i));
         }
-        if (options::getInt("training_threads", 1) > 0)
-            std::cout << "TRAIN: training threads are not built in this round (SURVEY.md 8(f) #1/#2)" << std::endl;
+        int n_training = options::getInt("training_threads", 1);
+        for (int i = 0; i < n_training; ++i) training.push_back(std::thread(&Selfplay::training_main, this, i));
     }
     void stop() {
         if (status.code() != RUNNING) throw std::runtime_error("stop() called when not running");
         status.code(WAITING);
         for (auto& t : inference) t.join();
+        for (auto& t : training) t.join();
         inference.clear();
+        training.clear();
         status.code(STOPPED);
     }
 
@@ -65,7 +70,7 @@ class Selfplay {
     std::string get_next_pgn() { throw std::runtime_error("PGN export is not built (thc SAN printing is out of scope)"); }
 
    private:
-    std::vector<std::thread> inference;
+    std::vector<std::thread> inference, training;
     NN* model;
     ReplayBuffer replay_buffer;
     int ibatch, nodes;
@@ -94,8 +99,13 @@ class Selfplay {
         kb_pool* pool = nullptr;
         kb_check(kb_pool_create(&pool, ibatch, options::getInt("b200_node_capacity", 1 << 18), &cfg));
         std::vector<float> obs((size_t)64 * OBSIZE), pi((size_t)64 * PSIZE), z(64);
+        auto partial = partial_trajectories.begin();
+        std::advance(partial, id);
         while (status.code() == RUNNING) {
             kb_check(kb_pool_step(pool, model->handle(), 64));
+            kb_pool_stats st;
+            kb_check(kb_pool_get_stats(pool, &st));
+            *partial = (int)(st.moves - st.samples);  // positions recorded in games still being played (selfplay.cpp:150-151)
             int m = 0;
             do {
                 kb_check(kb_pool_drain_samples(pool, 64, obs.data(), pi.data(), z.data(), &m));
@@ -104,6 +114,57 @@ class Selfplay {
         }
         kb_pool_destroy(pool);
         std::cout << "Terminating inference thread: " << id << std::endl;
+    }
+
+    // selfplay.cpp:215-304
+    void training_main(int id) {
+        std::cout << "TRAIN " << id << ": starting thread " << id << std::endl;
+        const std::string modelpath = options::getStr("model_path", "/tmp/model.pt");
+        const long cap = replay_buffer.size();
+        long target = cap, from = 0;  // train when count() reaches `target`; progress is shown relative to `from`
+        const int step = (int)(cap * options::getInt("rpb_train_pct", 40) / 100);
+        const int trajectories = (int)(cap * options::getInt("training_sample_pct", 60) / 100);
+        const bool detect_anomaly = options::getInt("training_detect_anomaly", 0) != 0;
+        if (detect_anomaly && !id) std::cout << "Anomaly detection enabled" << std::endl;
+        std::vector<float> inputs((size_t)trajectories * OBSIZE), visits((size_t)trajectories * PSIZE), results(trajectories);
+        while (status.code() == RUNNING) {
+            const long have = replay_buffer.count();
+            if (have < target) {
+                if (!id) {
+                    std::cout << "Gen " << model->get_generation() << " RPB " << 100 * (have - from) / (target - from) << "% [" << have - from << " / "
+                              << target - from << "] | Partials: ";
+                    int k = 0;
+                    for (auto& p : partial_trajectories) std::cout << " Inf " << k++ << ": " << p;
+                    std::cout << std::endl;
+                }
+                std::this_thread::sleep_for(std::chrono::milliseconds(1000));
+                continue;
+            }
+            std::cout << "TRAIN " << id << ": training generation " << model->get_generation() << " with " << trajectories
+                      << " trajectories sampled from last " << cap << std::endl;
+            NN candidate(model);
+            replay_buffer.select_batch(inputs.data(), visits.data(), results.data(), trajectories);
+            candidate.train(trajectories, inputs.data(), visits.data(), results.data(), detect_anomaly);
+            bool accepted = false;
+            try {
+                accepted = eval(model, &candidate, id);
+            } catch (std::exception& e) {
+                std::cerr << "TRAIN " << id << ": evaluation failed: " << e.what() << std::endl;
+            }
+            if (accepted) {
+                candidate.write(modelpath);
+                model->read(modelpath);
+                std::cout << "TRAIN " << id << ": candidate accepted: using new generation " << model->get_generation() << std::endl;
+                if (options::getInt("flush_old_rpb", 1)) replay_buffer.clear();
+                target = std::max(cap, replay_buffer.count() + (long)step);
+                from = replay_buffer.count();
+                continue;
+            }
+            std::cout << "TRAIN " << id << ": candidate rejected: generation remains " << model->get_generation() << std::endl;
+            from = replay_buffer.count();
+            target += step;
+        }
+        std::cout << "TRAIN " << id << ": stopping thread" << std::endl;
     }
 };
 }  // namespace kami

@@ -88,3 +88,18 @@ def test_arena_eval_smoke(kb):
     assert "model was updated during evaluation, skipping!" in text and "stale verdict 0" in text
     assert "evaluating model generation 1 over 3 games" in text and "arena verdict" in text
     assert "game 1 of 3" in text
+
+
+@pytest.mark.gpu
+def test_selfplay_train_arena_loop_smoke(kb):
+    """The whole loop of kami.cpp on small settings (kami/tests/selfplay_smoke.cpp): device self-play fills the
+    replay buffer, Selfplay::training_main (selfplay.cpp:215-304) clones, trains (CUDA step), runs the arena."""
+    exe = os.path.join(DROPIN, "selfplay_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("kami/_dropin not built")
+    out = subprocess.run([exe], capture_output=True, timeout=400)
+    text = out.stdout.decode()
+    assert out.returncode == 0, (out.stderr.decode()[-400:], text[-400:])
+    assert "TRAIN 0: training generation 0 with 48 trajectories" in text, text[-800:]
+    assert "EVAL 0: evaluating model generation 1" in text
+    assert ("candidate accepted" in text) or ("candidate rejected" in text)

@@ -449,3 +449,25 @@ def test_pool_step_legal_softmax_equals_dense_softmax_renormalised(kb, F, R):
     b.step(net, 24)
     same = sum(np.array_equal(a.tree(i).root_children()[1], b.tree(i).root_children()[1]) for i in range(n))
     assert same >= n - 2  # a prior that differs in the last bit may flip an exact PUCT tie
+
+
+def test_net_256_filters_full_size_batch_properties(kb):
+    """BASELINE config-3 size (1024+ boards, here 1100 = 158 items: some CTA pairs take two items, the item count
+    is even, the last item has one board) through the per-layer tcgen05 path (k_conv2 pairs): a subset of the
+    boards against the fp32 oracle, and the size-independent property that the network acts on boards
+    independently -- a permuted batch gives exactly the permuted outputs."""
+    F, R, B = 256, 2, 1100
+    params = NO.init_params(F, R, seed=31)
+    net = kb.NN(F, R)
+    net.load_blob(NO.pack_blob(params, F, R))
+    base = np.stack([e.observe() for e in H.sample_positions(100, seed=32)])
+    rng = np.random.RandomState(33)
+    obs = base[rng.randint(0, 100, size=B)]
+    pol, val = net.forward_full(obs)
+    assert np.abs(pol.sum(1) - 1).max() < 1e-4
+    pick = np.r_[0:6, 511:517, B - 6:B]
+    op, ov = NO.forward(params, obs[pick])
+    assert np.abs(val[pick] - ov).max() <= 1e-2 and _kl(op, pol[pick]) <= 1e-3
+    perm = rng.permutation(B)
+    pol2, val2 = net.forward_full(obs[perm])
+    assert np.array_equal(pol2, pol[perm]) and np.array_equal(val2, val[perm])
