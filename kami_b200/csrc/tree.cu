@@ -1290,6 +1290,9 @@ struct kb_pool {
     unsigned selects_since_compact;
     int policy_mode;  // kb_pool_step: 0 softmax over the legal moves only (default), 1 dense [n][4672] softmax
     cudaEvent_t ev[6];
+    cudaStream_t s_d2h, s_h2d;   // kb_pool_step_hostio: one copy stream per direction of the link
+    cudaEvent_t io_ev[12];
+    bool io_ready;
     cudaEvent_t evs[32][4];  // phase boundaries of up to 32 evenly spaced iterations of a kb_pool_step call
     bool evs_ready;
     kb_phase_ms last;
@@ -1409,6 +1412,11 @@ int kb_pool_destroy(kb_pool* p) {
     cudaFree(p->child_i); cudaFree(p->child_f); cudaFree(p->leaf_dev); cudaFree(p->policy_dev); cudaFree(p->value_dev);
     cudaFree(p->obs_batch_dev); cudaFree(d.dbg);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(p->ev[i]);
+    if (p->io_ready) {
+        cudaStreamDestroy(p->s_d2h);
+        cudaStreamDestroy(p->s_h2d);
+        for (int i = 0; i < 12; ++i) cudaEventDestroy(p->io_ev[i]);
+    }
     if (p->evs_ready)
         for (int i = 0; i < 32; ++i)
             for (int j = 0; j < 4; ++j) cudaEventDestroy(p->evs[i][j]);
@@ -1679,24 +1687,47 @@ int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, flo
     const size_t n = (size_t)p->d.n_trees;
     cudaStream_t st = main_stream();
     if (!p->obs_batch_dev) KB_CUDA(cudaMalloc(&p->obs_batch_dev, sizeof(float) * KB_OBSIZE * n));
+    if (!p->io_ready) {
+        KB_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+        KB_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+        for (int i = 0; i < 12; ++i) KB_CUDA(cudaEventCreateWithFlags(&p->io_ev[i], cudaEventDisableTiming));
+        p->io_ready = true;
+    }
     int r = net_reserve(net, (int)n);
     if (r) return r;
+    // Every array crosses the bus in both directions like in the reference (leaf observations out, NN::infer's host
+    // input in, its host policy / value out, MCTS::expand's host policy in).  The rows move in HOSTIO_CHUNKS pieces
+    // on a device->host and a host->device stream: piece c goes back up while piece c+1 is still coming down, so
+    // both directions of the link are busy at once; the data still passes through the caller's host buffers.
+    constexpr int HOSTIO_CHUNKS = 4;
+    cudaEvent_t ev_compute = p->io_ev[0], ev_back = p->io_ev[1];
+    cudaEvent_t* ev_piece = p->io_ev + 2;  // [HOSTIO_CHUNKS]
+    auto round_trip = [&](float* dev, float* host, size_t row_floats) -> int {
+        KB_CUDA(cudaEventRecord(ev_compute, st));
+        KB_CUDA(cudaStreamWaitEvent(p->s_d2h, ev_compute, 0));
+        for (int c = 0; c < HOSTIO_CHUNKS; ++c) {
+            const size_t r0 = n * c / HOSTIO_CHUNKS, r1 = n * (c + 1) / HOSTIO_CHUNKS;
+            if (r1 == r0) continue;
+            const size_t off = r0 * row_floats, bytes = (r1 - r0) * row_floats * sizeof(float);
+            KB_CUDA(cudaMemcpyAsync(host + off, dev + off, bytes, cudaMemcpyDeviceToHost, p->s_d2h));
+            KB_CUDA(cudaEventRecord(ev_piece[c], p->s_d2h));
+            KB_CUDA(cudaStreamWaitEvent(p->s_h2d, ev_piece[c], 0));
+            KB_CUDA(cudaMemcpyAsync(dev + off, host + off, bytes, cudaMemcpyHostToDevice, p->s_h2d));
+        }
+        KB_CUDA(cudaEventRecord(ev_back, p->s_h2d));
+        KB_CUDA(cudaStreamWaitEvent(st, ev_back, 0));
+        return KB_OK;
+    };
     for (int it = 0; it < iters; ++it) {
-        // select + Env::observe on the device, observations out to the caller's buffer
+        // select + Env::observe on the device; observations out to the caller's buffer and back in as NN::infer's input
         if ((r = pool_launch_select(p, nullptr, p->leaf_dev, st))) return r;
         if ((r = kb_encode_planes_dev((const kb_position*)p->leaf_dev, (int)n, p->obs_batch_dev))) return r;
-        KB_CUDA(cudaMemcpyAsync(obs_host, p->obs_batch_dev, sizeof(float) * KB_OBSIZE * n, cudaMemcpyDeviceToHost, st));
-        if ((r = pool_check(p, true))) return r;
-        // NN::infer(host obs) -> host policy / value
-        KB_CUDA(cudaMemcpyAsync(p->obs_batch_dev, obs_host, sizeof(float) * KB_OBSIZE * n, cudaMemcpyHostToDevice, st));
+        if ((r = round_trip(p->obs_batch_dev, obs_host, KB_OBSIZE))) return r;
         if ((r = obs_to_tall_launch(p->obs_batch_dev, (int)n, net_input_planes(net), st))) return r;
         if ((r = net_forward_async(net, net_input_planes(net), (int)n, p->policy_dev, p->value_dev, st))) return r;
-        KB_CUDA(cudaMemcpyAsync(policy_host, p->policy_dev, sizeof(float) * KB_PSIZE * n, cudaMemcpyDeviceToHost, st));
-        KB_CUDA(cudaMemcpyAsync(value_host, p->value_dev, sizeof(float) * n, cudaMemcpyDeviceToHost, st));  // vh.flat[i] (Q1)
-        KB_CUDA(cudaStreamSynchronize(st));
-        // MCTS::expand(host policy row, value)
-        KB_CUDA(cudaMemcpyAsync(p->policy_dev, policy_host, sizeof(float) * KB_PSIZE * n, cudaMemcpyHostToDevice, st));
-        KB_CUDA(cudaMemcpyAsync(p->value_dev, value_host, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+        // NN::infer's host policy / value out (value[i] = vh.flat[i], Q1), MCTS::expand's host policy row / value in
+        if ((r = round_trip(p->value_dev, value_host, 1))) return r;
+        if ((r = round_trip(p->policy_dev, policy_host, KB_PSIZE))) return r;
         k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 0, 0, 0);
         KB_CUDA(cudaGetLastError());
         p->launches += 4 + (unsigned long long)net_launches_per_forward(net);
