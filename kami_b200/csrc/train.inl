@@ -73,14 +73,23 @@ __device__ __forceinline__ void block_channel_sums(float (&a)[8], float (&q)[8],
 __global__ void __launch_bounds__(256) k_bn_stats(const uint4* pre, int boards, int slabs, float* sum, float* sumsq) {
     const int s = blockIdx.x, j = threadIdx.x & 7, pl = threadIdx.x >> 3;
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int npix = boards * 64;
-    for (int g = blockIdx.y * 32 + pl; g < npix; g += gridDim.y * 32) {
-        float f[8];
-        unpack8(pre[act_idx(g >> 6, g & 63, slabs, s, j)], f);
+    const int npix = boards * 64, stride = gridDim.y * 32;
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {  // four independent loads in flight per thread
+        uint4 v[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            a[k] += f[k];
-            q[k] = fmaf(f[k], f[k], q[k]);
+        for (int u = 0; u < 4; ++u) {
+            const int g = g0 + u * stride;
+            v[u] = g < npix ? pre[act_idx(g >> 6, g & 63, slabs, s, j)] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                a[k] += f[k];
+                q[k] = fmaf(f[k], f[k], q[k]);
+            }
         }
     }
     block_channel_sums(a, q, sum, sumsq, s * 64);
@@ -110,20 +119,27 @@ __global__ void __launch_bounds__(256) k_bn_apply(const uint4* pre, uint4* post,
         sc[k] = gamma[c0 + k] * rstd[c0 + k];
         sh[k] = beta[c0 + k] - mean[c0 + k] * sc[k];
     }
-    const int npix = boards * 64;
-    for (int g = blockIdx.y * 32 + pl; g < npix; g += gridDim.y * 32) {
-        const size_t i = act_idx(g >> 6, g & 63, slabs, s, j);
-        float f[8];
-        unpack8(pre[i], f);
+    const int npix = boards * 64, stride = gridDim.y * 32;
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
+        size_t idx[4];
+        uint4 v[4], sk[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.0f);
-        if (skip) {
-            float t[8];
-            unpack8(skip[i], t);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] += t[k];
+        for (int u = 0; u < 4; ++u) {
+            const int g = g0 + u * stride;
+            idx[u] = g < npix ? act_idx(g >> 6, g & 63, slabs, s, j) : 0;
+            v[u] = pre[idx[u]];
+            sk[u] = skip ? skip[idx[u]] : make_uint4(0, 0, 0, 0);
         }
-        post[i] = pack8(f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (g0 + u * stride >= npix) break;
+            float f[8], t[8];
+            unpack8(v[u], f);
+            unpack8(sk[u], t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.0f) + t[k];
+            post[idx[u]] = pack8(f);
+        }
     }
 }
 
@@ -142,18 +158,28 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const uint4* dy, const ui
         be[k] = beta[c0 + k];
     }
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int npix = boards * 64;
-    for (int g = blockIdx.y * 32 + pl; g < npix; g += gridDim.y * 32) {
-        const size_t i = act_idx(g >> 6, g & 63, slabs, s, j);
-        float x[8], d[8];
-        unpack8(pre[i], x);
-        unpack8(dy[i], d);
+    const int npix = boards * 64, stride = gridDim.y * 32;
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
+        uint4 vx[4], vd[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float xh = (x[k] - mu[k]) * rs[k];
-            const float dm = fmaf(ga[k], xh, be[k]) > 0.0f ? d[k] : 0.0f;
-            a[k] += dm;
-            q[k] = fmaf(dm, xh, q[k]);
+        for (int u = 0; u < 4; ++u) {
+            const int g = g0 + u * stride;
+            const size_t i = g < npix ? act_idx(g >> 6, g & 63, slabs, s, j) : 0;
+            vx[u] = pre[i];
+            vd[u] = g < npix ? dy[i] : make_uint4(0, 0, 0, 0);  // a zero gradient adds nothing to either sum
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float x[8], d[8];
+            unpack8(vx[u], x);
+            unpack8(vd[u], d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = (x[k] - mu[k]) * rs[k];
+                const float dm = fmaf(ga[k], xh, be[k]) > 0.0f ? d[k] : 0.0f;
+                a[k] += dm;
+                q[k] = fmaf(dm, xh, q[k]);
+            }
         }
     }
     block_channel_sums(a, q, s1, s2, s * 64);
@@ -173,19 +199,31 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const uint4* dy, const uin
         m1[k] = s1[c0 + k] / n;
         m2[k] = s2[c0 + k] / n;
     }
-    const int npix = boards * 64;
-    for (int g = blockIdx.y * 32 + pl; g < npix; g += gridDim.y * 32) {
-        const size_t i = act_idx(g >> 6, g & 63, slabs, s, j);
-        float x[8], d[8], o[8];
-        unpack8(pre[i], x);
-        unpack8(dy[i], d);
+    const int npix = boards * 64, stride = gridDim.y * 32;
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
+        size_t idx[4];
+        uint4 vx[4], vd[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float xh = (x[k] - mu[k]) * rs[k];
-            const float dm = fmaf(ga[k], xh, be[k]) > 0.0f ? d[k] : 0.0f;
-            o[k] = ga[k] * rs[k] * (dm - m1[k] - xh * m2[k]);
+        for (int u = 0; u < 4; ++u) {
+            const int g = g0 + u * stride;
+            idx[u] = g < npix ? act_idx(g >> 6, g & 63, slabs, s, j) : 0;
+            vx[u] = pre[idx[u]];
+            vd[u] = dy[idx[u]];
         }
-        dpre[i] = pack8(o);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (g0 + u * stride >= npix) break;
+            float x[8], d[8], o[8];
+            unpack8(vx[u], x);
+            unpack8(vd[u], d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = (x[k] - mu[k]) * rs[k];
+                const float dm = fmaf(ga[k], xh, be[k]) > 0.0f ? d[k] : 0.0f;
+                o[k] = ga[k] * rs[k] * (dm - m1[k] - xh * m2[k]);
+            }
+            dpre[idx[u]] = pack8(o);
+        }
     }
 }
 // dgamma = s2, dbeta = s1; clears the accumulators
@@ -684,7 +722,7 @@ int t_repack(kb_trainer* t, cudaStream_t st) {
 }
 
 dim3 bn_grid(int slabs, int boards) {
-    int y = (boards * 64 + 31) / 32;
+    int y = (boards * 64 + 127) / 128;  // four pixels per thread and trip
     if (y > 592) y = 592;
     return dim3(slabs, y > 0 ? y : 1);
 }
