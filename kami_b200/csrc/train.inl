@@ -263,6 +263,7 @@ struct WgradParams {
     const uint8_t* dy;  // [items][co_slabs] slabs, gradient w.r.t. the conv output (pads and idle boards are zero)
     const uint8_t* x;   // [items][ci_slabs] slabs, the conv input
     float* dw;          // fp32 [O][I][ntaps], accumulated with red.global.add
+    float* part;        // k_wgrad_row: per-subset partial sums [subset][tap][ci][co] (reduced by k_wgrad_reduce), or nullptr
     int items, co_slabs, ci_slabs, O, I, ntaps, subsets;
 };
 constexpr int WG_KC = 64;                      // pixels (K rows) per stage
@@ -389,6 +390,156 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradParams P) {
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- wgrad of the 3x3 convolutions, one kernel ROW per CTA ----------------------------------------------------
+// k_wgrad re-streams the activations once per tap: 68 KB of operands for 8 MMAs of 128 cycles = 66 B/clk per SM
+// against an L2 -> SM cap of ~42 (ncu: 867 MB per launch, tensor pipe 45 % active).  Here a CTA owns the three
+// taps of one kernel row for a (128 co) x (128 ci) block: D = 3 x [128 x 128] fp32 (384 TMEM columns).  The three
+// taps read the SAME dy chunk and x windows one line apart, so a stage is 16 KB of dy + a 66-line x window
+// (16.5 KB) for 12 MMAs of 64 cycles: 43 B/clk -- the L2 stream and the tensor pipe now take the same time.
+constexpr int WR_B_SLAB = 10240;                      // >= (7 + 66) lines, multiple of 1024
+constexpr int WR_STAGE = 2 * WG_A_SLAB + 2 * WR_B_SLAB;  // 36 KB
+constexpr int WR_NSTAGE = 5;
+constexpr int WR_SMEM = 1024 + WR_NSTAGE * WR_STAGE;
+static_assert(WR_SMEM <= 232448 && WR_STAGE % 1024 == 0, "wgrad-row shared memory");
+
+__global__ void __launch_bounds__(256, 1) k_wgrad_row(const WgradParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = ptx::uniform_warp_id(), lane = threadIdx.x & 31;
+    const uint32_t bar0 = ptx::smem_u32(smem);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (8 + s); };
+    const uint32_t t_full = bar0 + 8u * 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    const uint32_t stage0 = bar0 + 1024;
+    const int co_halves = (P.co_slabs + 1) / 2, ci_halves = (P.ci_slabs + 1) / 2;
+    const int kinds = 3 * co_halves * ci_halves;
+    const int kind = (int)blockIdx.x % kinds, subset = (int)blockIdx.x / kinds;
+    const int row = kind % 3, coh = (kind / 3) % co_halves, cih = kind / (3 * co_halves);
+    const int dyk = row - 1;
+    const int nco = P.co_slabs - 2 * coh < 2 ? P.co_slabs - 2 * coh : 2, nci = P.ci_slabs - 2 * cih < 2 ? P.ci_slabs - 2 * cih : 2;
+    const int N = 64 * nci;
+    const int my_items = P.items > subset ? (P.items - 1 - subset) / P.subsets + 1 : 0;
+    constexpr int CHUNKS = SLAB_PIX / WG_KC;  // 10
+    constexpr int B_BYTES = (WG_KC + 2) * LINE_BYTES;  // 66-line window: the rows of the taps dx = -1, 0, +1
+    const int total = my_items * CHUNKS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WR_NSTAGE; ++s) {
+            ptx::mbar_init(full(s), 1);
+            ptx::mbar_init(empty(s), 1);
+        }
+        ptx::mbar_init(t_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer =====
+        int stage = 0, phase = 0;
+        for (int c = 0; c < total; ++c) {
+            const int ii = c / CHUNKS, k0 = (c - ii * CHUNKS) * WG_KC;
+            const int item = subset + ii * P.subsets;
+            const int p0 = k0 + dyk * TALL_PITCH - 1, ph = p0 & 7;  // first line of the x window; two's complement handles p0 < 0
+            ptx::mbar_wait(empty(stage), phase ^ 1);
+            if (ptx::elect_one()) {
+                const uint32_t sa = stage0 + stage * WR_STAGE, sb = sa + 2 * WG_A_SLAB;
+                ptx::mbar_arrive_expect_tx(full(stage), (uint32_t)nco * WG_A_SLAB + (uint32_t)nci * B_BYTES);
+                for (int s = 0; s < nco; ++s)
+                    ptx::bulk_g2s(sa + s * WG_A_SLAB, P.dy + ((size_t)item * P.co_slabs + 2 * coh + s) * SLAB_BYTES + (size_t)k0 * LINE_BYTES, WG_A_SLAB,
+                                  full(stage));
+                for (int s = 0; s < nci; ++s)
+                    ptx::bulk_g2s(sb + s * WR_B_SLAB + ph * LINE_BYTES,
+                                  P.x + ((ptrdiff_t)((size_t)item * P.ci_slabs + 2 * cih + s) * SLAB_BYTES + (ptrdiff_t)p0 * LINE_BYTES), B_BYTES, full(stage));
+            }
+            __syncwarp();
+            if (++stage == WR_NSTAGE) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D[tap][128 co x N ci], A and B MN-major =====
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        int stage = 0, phase = 0;
+        for (int c = 0; c < total; ++c) {
+            const int ii = c / CHUNKS, k0 = (c - ii * CHUNKS) * WG_KC;
+            const int ph = (k0 + dyk * TALL_PITCH - 1) & 7;
+            ptx::mbar_wait(full(stage), phase);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t sa = stage0 + stage * WR_STAGE, sb = sa + 2 * WG_A_SLAB + ph * LINE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < WG_KC / 16; ++kk) {
+                    const uint64_t adesc = wg_desc(sa + kk * 16 * LINE_BYTES, WG_A_SLAB, 1024);
+#pragma unroll
+                    for (int tp = 0; tp < 3; ++tp)  // tap dx = tp - 1 starts tp lines into the window
+                        ptx::mma_bf16(tmem_base + tp * 128, adesc, wg_desc(sb + (tp + kk * 16) * LINE_BYTES, WR_B_SLAB, 1024), idesc,
+                                      (c | kk) == 0 ? 0u : 1u);
+                }
+                ptx::mma_commit(empty(stage));
+                if (c == total - 1) ptx::mma_commit(t_full);
+            }
+            __syncwarp();
+            if (++stage == WR_NSTAGE) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    } else if (warp >= 4 && total > 0) {
+        // ===== epilogue: TMEM -> red.global.add into dw[co][ci][tap] =====
+        const int q = warp & 3;
+        ptx::mbar_wait(t_full, 0);
+        ptx::tc_fence_after();
+        const int co = coh * 128 + 32 * q + lane;
+        const int COP = 64 * P.co_slabs, CIP = 64 * P.ci_slabs;  // padded extents of the partial buffer
+        for (int tp = 0; tp < 3; ++tp) {
+            const int tap = row * 3 + tp;
+            for (int cg = 0; cg < N / 16; ++cg) {
+                uint32_t v[16];
+                ptx::tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + tp * 128 + cg * 16, v);
+                ptx::tmem_ld_wait();
+                if (32 * q + lane < 64 * nco) {
+                    if (P.part) {  // plain stores, consecutive lanes = consecutive co: one 128-byte line per warp store
+                        float* dst = P.part + (((size_t)subset * 9 + tap) * CIP + (cih * 128 + cg * 16)) * COP + co;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[(size_t)i * COP] = __uint_as_float(v[i]);
+                    } else if (co < P.O) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int ci = cih * 128 + cg * 16 + i;
+                            if (ci < P.I) atomicAdd(P.dw + ((size_t)co * P.I + ci) * 9 + tap, __uint_as_float(v[i]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// dw[co][ci][tap] = sum over subsets of part[subset][tap][ci][co]  (reads coalesced along co)
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* part, int subsets, int COP, int CIP, int O, int I, float* dw) {
+    const size_t per = (size_t)9 * CIP * COP;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < per; e += (size_t)gridDim.x * 256) {
+        const int co = (int)(e % COP);
+        const int ci = (int)((e / COP) % CIP);
+        const int tap = (int)(e / ((size_t)COP * CIP));
+        if (co >= O || ci >= I) continue;
+        float s = 0.0f;
+        for (int k = 0; k < subsets; ++k) s += part[(size_t)k * per + e];
+        dw[((size_t)co * I + ci) * 9 + tap] = s;
+    }
 }
 
 // ---- policy head: softmax, loss and dlogits (nn.cpp:80, 98-102) -----------------------------------------
@@ -664,6 +815,8 @@ struct kb_trainer {
     float *vpre = nullptr, *vact = nullptr, *dfc = nullptr, *dvn = nullptr, *vstats = nullptr;
     float *acc = nullptr;     // [2][256] channel accumulators + [4] value-head scalars + [1] loss
     float *zeros = nullptr;   // 256 zero biases for the dgrad convs
+    float *wpart = nullptr;   // k_wgrad_row partial sums: [subsets <= 49][9][<= 256][<= 256]
+    size_t wpart_floats = 0;
     float last_loss = 0.0f;
 };
 
@@ -743,6 +896,34 @@ int t_wgrad(kb_trainer* t, const TConv& c, const uint4* dy, const uint4* x, int 
     p.O = c.O;
     p.I = c.I;
     p.ntaps = c.k * c.k;
+    p.part = nullptr;
+    static int use_row = -1;
+    if (use_row < 0) {
+        const char* e = getenv("KB_WGRAD_PER_TAP");
+        use_row = (e && e[0] == '1') ? 0 : 1;
+    }
+    if (p.ntaps == 9 && use_row) {  // one kernel row (three taps) x 128 co x 128 ci per CTA
+        static bool configured_row = false;
+        if (!configured_row) {
+            KB_CUDA(cudaFuncSetAttribute(k_wgrad_row, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM));
+            configured_row = true;
+        }
+        const int kinds = 3 * ((p.co_slabs + 1) / 2) * ((p.ci_slabs + 1) / 2);
+        int subsets = sm_count() / kinds;
+        if (subsets > p.items) subsets = p.items;
+        if (subsets < 1) subsets = 1;
+        p.subsets = subsets;
+        const int COP = 64 * p.co_slabs, CIP = 64 * p.ci_slabs;
+        const size_t need = (size_t)subsets * 9 * CIP * COP;
+        p.part = need <= t->wpart_floats ? t->wpart : nullptr;  // too many subsets for the scratch: fall back to atomics
+        k_wgrad_row<<<kinds * subsets, 256, WR_SMEM, st>>>(p);
+        KB_CUDA(cudaGetLastError());
+        if (p.part) {
+            k_wgrad_reduce<<<592, 256, 0, st>>>(p.part, subsets, COP, CIP, p.O, p.I, p.dw);
+            KB_CUDA(cudaGetLastError());
+        }
+        return KB_OK;
+    }
     int subsets = sm_count() / p.ntaps;
     if (subsets > p.items) subsets = p.items;
     if (subsets < 1) subsets = 1;
@@ -878,6 +1059,14 @@ int kb_trainer_create(kb_trainer** out, int filters, int residuals, int max_batc
     t->zeros = (float*)p;
     T_TRY(t_alloc(t, &p, sizeof(float) * 520, false));
     t->acc = (float*)p;
+    {
+        const int halves = (filters / 64 + 1) / 2, kinds = 3 * halves * halves;
+        int subsets = sm_count() / kinds;
+        if (subsets < 1) subsets = 1;
+        t->wpart_floats = (size_t)subsets * 9 * filters * filters;
+        T_TRY(t_alloc(t, &p, sizeof(float) * t->wpart_floats, false));
+        t->wpart = (float*)p;
+    }
     size_t off = 0;
     auto add_conv = [&](int O, int I, int k, bool bn, int in_slabs, int ksteps, bool dgrad, bool save) -> int {
         TConv c;
