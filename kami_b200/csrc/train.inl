@@ -94,30 +94,29 @@ __global__ void __launch_bounds__(256) k_bn_stats(const uint4* pre, int boards, 
     }
     block_channel_sums(a, q, sum, sumsq, s * 64);
 }
-// mean / rstd of the batch; running statistics with momentum 0.1 and the unbiased variance (LibTorch
-// BatchNorm2d defaults); clears the accumulators for the next use
-__global__ void k_bn_finalize(float* sum, float* sumsq, int C, float n, float* mean, float* rstd, float* run_mean, float* run_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const float m = sum[c] / n;
-    const float var = fmaxf(sumsq[c] / n - m * m, 0.0f);
-    mean[c] = m;
-    rstd[c] = rsqrtf(var + BN_EPS_T);
-    run_mean[c] = (1.0f - BN_MOMENTUM_T) * run_mean[c] + BN_MOMENTUM_T * m;
-    run_var[c] = (1.0f - BN_MOMENTUM_T) * run_var[c] + BN_MOMENTUM_T * var * (n / fmaxf(n - 1.0f, 1.0f));
-    sum[c] = 0.0f;
-    sumsq[c] = 0.0f;
-}
 // post = relu(gamma * xhat + beta) (+ skip): nn.cpp:28-33, 63-65, 72-74
-__global__ void __launch_bounds__(256) k_bn_apply(const uint4* pre, uint4* post, const uint4* skip, int boards, int slabs, const float* mean,
-                                                  const float* rstd, const float* gamma, const float* beta) {
+// sum / sumsq: this layer's own accumulators (zeroed once per step).  Every thread derives mean / rstd of its 8
+// channels; blocks with blockIdx.y == 0 publish them for the backward pass and update the running statistics
+// (momentum 0.1, unbiased variance: LibTorch BatchNorm2d defaults).
+__global__ void __launch_bounds__(256) k_bn_apply(const uint4* pre, uint4* post, const uint4* skip, int boards, int slabs, const float* sum,
+                                                  const float* sumsq, float n, float* mean, float* rstd, float* run_mean, float* run_var,
+                                                  const float* gamma, const float* beta) {
     const int s = blockIdx.x, j = threadIdx.x & 7, pl = threadIdx.x >> 3;
     const int c0 = s * 64 + j * 8;
     float sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        sc[k] = gamma[c0 + k] * rstd[c0 + k];
-        sh[k] = beta[c0 + k] - mean[c0 + k] * sc[k];
+        const float m = sum[c0 + k] / n;
+        const float var = fmaxf(sumsq[c0 + k] / n - m * m, 0.0f);
+        const float rs = rsqrtf(var + BN_EPS_T);
+        sc[k] = gamma[c0 + k] * rs;
+        sh[k] = beta[c0 + k] - m * sc[k];
+        if (blockIdx.y == 0 && pl == 0) {
+            mean[c0 + k] = m;
+            rstd[c0 + k] = rs;
+            run_mean[c0 + k] = (1.0f - BN_MOMENTUM_T) * run_mean[c0 + k] + BN_MOMENTUM_T * m;
+            run_var[c0 + k] = (1.0f - BN_MOMENTUM_T) * run_var[c0 + k] + BN_MOMENTUM_T * var * (n / fmaxf(n - 1.0f, 1.0f));
+        }
     }
     const int npix = boards * 64, stride = gridDim.y * 32;
     for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
@@ -186,7 +185,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const uint4* dy, const ui
 }
 // dpre = gamma * rstd * (dy*mask - s1/n - xhat * s2/n)
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const uint4* dy, const uint4* pre, uint4* dpre, int boards, int slabs, const float* mean,
-                                                      const float* rstd, const float* gamma, const float* beta, const float* s1, const float* s2, float n) {
+                                                      const float* rstd, const float* gamma, const float* beta, const float* s1, const float* s2, float n,
+                                                      float* dgamma, float* dbeta) {
     const int s = blockIdx.x, j = threadIdx.x & 7, pl = threadIdx.x >> 3;
     const int c0 = s * 64 + j * 8;
     float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
@@ -198,6 +198,10 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const uint4* dy, const uin
         be[k] = beta[c0 + k];
         m1[k] = s1[c0 + k] / n;
         m2[k] = s2[c0 + k] / n;
+        if (blockIdx.y == 0 && pl == 0) {  // dgamma = sum(dy * mask * xhat), dbeta = sum(dy * mask)
+            dgamma[c0 + k] = s2[c0 + k];
+            dbeta[c0 + k] = s1[c0 + k];
+        }
     }
     const int npix = boards * 64, stride = gridDim.y * 32;
     for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
@@ -226,16 +230,6 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const uint4* dy, const uin
         }
     }
 }
-// dgamma = s2, dbeta = s1; clears the accumulators
-__global__ void k_bn_bwd_finalize(float* s1, float* s2, int C, float* dgamma, float* dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    dgamma[c] = s2[c];
-    dbeta[c] = s1[c];
-    s1[c] = 0.0f;
-    s2[c] = 0.0f;
-}
-
 // ---- weight packing (fp32 master -> bf16 operand blocks of k_conv / k_conv2) -------------------------
 // Logical conv: out channel o, in channel ci, tap t.  transpose_flip = 0: w[o][ci][t] (forward);
 // 1: w[ci][o][taps-1-t] (the dgrad conv: in/out swapped, kernel rotated by 180 degrees).
@@ -797,6 +791,7 @@ struct TConv {            // one convolution of the network and everything the s
     bool has_dgrad = false;
     uint4 *pre = nullptr, *post = nullptr;  // saved activations (bf16 tall layout)
     float *mean = nullptr, *rstd = nullptr; // batch statistics [O]
+    float *accum = nullptr;                 // this layer's [4][O] sums: forward sum / sumsq, backward s1 / s2 (zeroed once per step)
     int out_slabs = 0, in_slabs = 0;
 };
 
@@ -813,7 +808,9 @@ struct kb_trainer {
     uint4 *P = nullptr, *dlogits = nullptr, *dH = nullptr, *dXa = nullptr, *dXb = nullptr, *dpre = nullptr, *dpre2 = nullptr;
     float *logits = nullptr, *obs_dev = nullptr, *pi_dev = nullptr, *z_dev = nullptr;
     float *vpre = nullptr, *vact = nullptr, *dfc = nullptr, *dvn = nullptr, *vstats = nullptr;
-    float *acc = nullptr;     // [2][256] channel accumulators + [4] value-head scalars + [1] loss
+    float *acc = nullptr;     // [2][256] scratch + [4] value-head scalars + [1] loss
+    float *bn_arena = nullptr; // every BatchNorm layer's [4][O] accumulators, one memset per step
+    size_t bn_arena_floats = 0;
     float *zeros = nullptr;   // 256 zero biases for the dgrad convs
     float *wpart = nullptr;   // k_wgrad_row partial sums: [subsets <= 49][9][<= 256][<= 256]
     size_t wpart_floats = 0;
@@ -936,11 +933,11 @@ int t_wgrad(kb_trainer* t, const TConv& c, const uint4* dy, const uint4* x, int 
 // BatchNorm + ReLU backward of conv c: dy (w.r.t. the ReLU output) -> dpre_out; gamma/beta gradients
 int t_bn_bwd(kb_trainer* t, const TConv& c, const uint4* dy, uint4* dpre_out, cudaStream_t st) {
     const float n = (float)t->batch * 64.0f;
-    float *s1 = t->acc, *s2 = t->acc + 256;
+    float *s1 = c.accum + 2 * c.O, *s2 = c.accum + 3 * c.O;
     const float *g = t->params + c.g_off, *be = t->params + c.be_off;
     k_bn_bwd_reduce<<<bn_grid(c.out_slabs, t->batch), 256, 0, st>>>(dy, c.pre, t->batch, c.out_slabs, c.mean, c.rstd, g, be, s1, s2);
-    k_bn_bwd_apply<<<bn_grid(c.out_slabs, t->batch), 256, 0, st>>>(dy, c.pre, dpre_out, t->batch, c.out_slabs, c.mean, c.rstd, g, be, s1, s2, n);
-    k_bn_bwd_finalize<<<(c.O + 127) / 128, 128, 0, st>>>(s1, s2, c.O, t->grads + c.g_off, t->grads + c.be_off);
+    k_bn_bwd_apply<<<bn_grid(c.out_slabs, t->batch), 256, 0, st>>>(dy, c.pre, dpre_out, t->batch, c.out_slabs, c.mean, c.rstd, g, be, s1, s2, n,
+                                                                   t->grads + c.g_off, t->grads + c.be_off);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
@@ -950,11 +947,10 @@ int t_conv_bn_fwd(kb_trainer* t, TConv& c, const uint4* in, const uint4* skip, c
     int r = run_conv(c.fwd, in, c.pre, nullptr, nullptr, t->batch, st);
     if (r) return r;
     const float n = (float)t->batch * 64.0f;
-    float *s1 = t->acc, *s2 = t->acc + 256;
+    float *s1 = c.accum, *s2 = c.accum + c.O;
     k_bn_stats<<<bn_grid(c.out_slabs, t->batch), 256, 0, st>>>(c.pre, t->batch, c.out_slabs, s1, s2);
-    k_bn_finalize<<<(c.O + 127) / 128, 128, 0, st>>>(s1, s2, c.O, n, c.mean, c.rstd, t->params + c.rm_off, t->params + c.rv_off);
-    k_bn_apply<<<bn_grid(c.out_slabs, t->batch), 256, 0, st>>>(c.pre, c.post, skip, t->batch, c.out_slabs, c.mean, c.rstd, t->params + c.g_off,
-                                                               t->params + c.be_off);
+    k_bn_apply<<<bn_grid(c.out_slabs, t->batch), 256, 0, st>>>(c.pre, c.post, skip, t->batch, c.out_slabs, s1, s2, n, c.mean, c.rstd,
+                                                               t->params + c.rm_off, t->params + c.rv_off, t->params + c.g_off, t->params + c.be_off);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
@@ -977,6 +973,7 @@ int t_forward_backward(kb_trainer* t, const float* obs_dev, const float* pi_dev,
     float* loss = t->acc + 516;
     float* vsum = t->acc + 512;
     KB_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(float) * 520, st));
+    KB_CUDA(cudaMemsetAsync(t->bn_arena, 0, sizeof(float) * t->bn_arena_floats, st));
     // ---------------- forward ----------------
     if ((r = obs_to_tall_launch(obs_dev, batch, t->P, st))) return r;
     if ((r = t_conv_bn_fwd(t, t->conv[0], t->P, nullptr, st))) return r;
@@ -1112,6 +1109,18 @@ int kb_trainer_create(kb_trainer** out, int filters, int residuals, int max_batc
     }
     T_TRY(add_conv(128, F, 1, true, fs, 4, true, true));
     T_TRY(add_conv(73, 128, 1, false, 2, 4, true, false));
+    for (auto& c : t->conv)
+        if (c.bn) t->bn_arena_floats += 4 * (size_t)c.O;
+    T_TRY(t_alloc(t, &p, sizeof(float) * t->bn_arena_floats, false));
+    t->bn_arena = (float*)p;
+    {
+        size_t o = 0;
+        for (auto& c : t->conv)
+            if (c.bn) {
+                c.accum = t->bn_arena + o;
+                o += 4 * (size_t)c.O;
+            }
+    }
     t->vw_off = off;
     off += F;
     t->vb_off = off;
