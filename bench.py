@@ -349,7 +349,36 @@ def train_leg(api, L, dist, local, world, pool, F=256, R=20, B=1024, steps=5):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local):
+    """Best effort: run this rank (and first-touch its pinned host buffers) on the NUMA node the GPU hangs off, so the
+    host-buffer path does not cross sockets.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]  # 0000:xx:yy.z
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:  # never lose the bench to this
+        return "not bound (%s)" % type(e).__name__
+
+
 def run_ours(args, rank, world, local, dist):
+    numa = bind_to_gpu_numa(local)
     import kami_b200
     from kami_b200 import api
     from kami_b200.parallel import per_rank_seed
@@ -496,6 +525,7 @@ def run_ours(args, rank, world, local, dist):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps},
         "gpu_launches": int(st["kernel_launches"]),
+        "host_numa_binding": numa,
         "clocks": clocks,
     }
     if cpu:

@@ -99,6 +99,30 @@ int ref_nn_train(void* p, int n, float* inputs, float* obs_p, float* obs_v, int 
     return h->nn->get_generation();
 }
 
+// NN::write / NN::read (kami/nn/nn.cpp:189-222): the reference's torch-archive checkpoint incl. "generation"
+int ref_nn_write(void* p, const char* path) {
+    std::cout.setstate(std::ios_base::failbit);
+    try {
+        ((Handle*)p)->nn->write(path);
+    } catch (std::exception& e) {
+        std::cout.clear();
+        return -1;
+    }
+    std::cout.clear();
+    return 0;
+}
+int ref_nn_read(void* p, const char* path) {
+    Handle* h = (Handle*)p;
+    try {
+        h->nn->read(path);
+    } catch (...) {
+        return -1;
+    }
+    collect(h);
+    return 0;
+}
+int ref_nn_generation(void* p) { return ((Handle*)p)->nn->get_generation(); }
+
 int ref_nn_num_tensors(void* p) { return (int)((Handle*)p)->tensors.size(); }
 // Returns numel; writes name and up to 4 dims (rank returned through *rank).
 long ref_nn_tensor_info(void* p, int i, char* name, int cap, long* dims, int* rank, int* is_int64) {

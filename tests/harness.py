@@ -401,6 +401,9 @@ def ref_nn_lib():
         L.ref_nn_tensor_get.argtypes = [C.c_void_p, C.c_int, c_float_p]
         L.ref_nn_tensor_set.argtypes = [C.c_void_p, C.c_int, c_float_p]
         L.ref_nn_set_threads.argtypes = [C.c_int]
+        L.ref_nn_write.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_nn_read.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_nn_generation.argtypes = [C.c_void_p]
         L.ref_nn_train.argtypes = [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
         _refnn = L
     return _refnn
@@ -462,6 +465,17 @@ class RefNN:
         val = np.zeros((B, 256), np.float32)
         self.L.ref_nn_forward_full(self.h, _fp(obs), B, _fp(pol), _fp(val))
         return pol, val
+
+    def write(self, path):
+        if self.L.ref_nn_write(self.h, str(path).encode()) != 0:
+            raise RuntimeError("reference NN::write threw")
+
+    def read(self, path):
+        if self.L.ref_nn_read(self.h, str(path).encode()) != 0:
+            raise RuntimeError("reference NN::read threw")
+
+    def generation(self):
+        return self.L.ref_nn_generation(self.h)
 
     def train(self, obs, obs_p, obs_v, mlr, epochs, batchsize):
         """NN::train (nn.cpp:224-377); returns the new generation."""
