@@ -225,7 +225,8 @@ KB_HDN void start_position(Pos& p) {  // position.c:19-36
 
 // position.c:167-321.  `next` = position after `mv`; returns whether the mover's king is
 // safe.  WITH_CHECK also computes next.check (only needed for positions that are kept).
-template <bool WITH_CHECK>
+// KNOWN_LEGAL: the move comes from a legal-action list (tree descent), the king-safety test is skipped.
+template <bool WITH_CHECK, bool KNOWN_LEGAL = false>
 KB_HD bool make_move(const Pos& cur, u16 mv, Pos& next) {
     next = cur;
     const int src = (mv >> 6) & 63, dst = mv & 63, promo = mv >> 12;
@@ -266,12 +267,19 @@ KB_HD bool make_move(const Pos& cur, u16 mv, Pos& next) {
     next.ply = (u16)(cur.ply + 1);
     u64 occ = occ_all(next);
     u64 own = us == WHITE ? next.white : (occ ^ next.white);
-    if (any_attacked(next, next.pc[KING] & own, us ^ 1)) return false;
+    if (!KNOWN_LEGAL && any_attacked(next, next.pc[KING] & own, us ^ 1)) return false;
     if (WITH_CHECK) {
         set_full_key(next);
         next.check = any_attacked(next, next.pc[KING] & (occ ^ own), us) ? 1 : 0;
     }
     return true;
+}
+
+// position.c:316-319: is the side to move in check
+KB_HD u8 in_check(const Pos& p) {
+    const u64 occ = occ_all(p);
+    const u64 own = p.ctm == WHITE ? p.white : (occ ^ p.white);
+    return any_attacked(p, p.pc[KING] & own, p.ctm ^ 1) ? 1 : 0;
 }
 
 // ---- pseudo-legal generation, reference emission order (position.c:360-561, 563-740) -------

@@ -250,8 +250,12 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
             m = __shfl_sync(0xffffffffu, bcm, src);
         }
         const int action = (int)(m & 0xFFFF);
+        // Children were created from legal actions, so the king-safety test is skipped; the check flag is only
+        // needed at the leaf (movegen, Env::terminal) and is computed once after the descent.  The full key is
+        // needed at every level (repetition history).
         Pos nx;
-        make_move<true>(pos, decode_action(pos, action), nx);
+        make_move<false, true>(pos, decode_action(pos, action), nx);
+        set_full_key(nx);
         if (lane == 0) {
             c.hist[nh] = pos.key;
             c.path[depth + 1] = child;
@@ -262,6 +266,7 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
         cur = child;
         turn = child_turn;
     }
+    if (depth > 0) pos.check = in_check(pos);
     __syncwarp();
     if (lane == 0 && scanned) atomicAdd(&P.stats->children_scanned, scanned);
     // A node is one move sequence from the game start, so its terminal status never changes: the
