@@ -608,7 +608,33 @@ KB_HD u64 backward_pawns(u64 own_pawns, u64 opp_pawns, int col) {  // board.c:29
     stops &= oa;
     return shl(stops, col == WHITE ? -8 : 8);
 }
-KB_HDN int static_eval(const Pos& p) {
+// The guard terms of the eval (centre control, king zones: position.c:1110-1145) are 20 independent
+// attackers_to() evaluations -- four fifths of the eval's work.  Term i in [0, 20): 0..3 the centre squares,
+// 4..11 the i-th square of the white king's zone, 12..19 of the black king's zone (absent squares add 0).
+constexpr int EVAL_GUARD_TERMS = 20;
+KB_HD u64 nth_bit(u64 b, int n) {
+    for (int i = 0; i < n; ++i) b &= b - 1;
+    return b & (~b + 1);
+}
+KB_HD void eval_guard_term(const Pos& p, int i, int& mg, int& eg) {
+    const u64 occ = occ_all(p), W = p.white;
+    if (i < 4) {
+        const int sq = i == 0 ? 27 : i == 1 ? 28 : i == 2 ? 35 : 36;
+        const int v = guard_value(p, sq, occ);
+        mg += v * 20;
+        eg += v * 8;
+        return;
+    }
+    const bool white_zone = i < 12;
+    const u64 king = p.pc[KING] & (white_zone ? W : (occ ^ W));
+    const u64 one = nth_bit(king_attacks(lsb(king)), white_zone ? i - 4 : i - 12);
+    if (!one) return;
+    int g = guard_value(p, lsb(one), occ);
+    if (white_zone ? g > 0 : g < 0) g = 0;
+    mg += g * 7;
+    eg += g * 6;
+}
+KB_HDN int static_eval(const Pos& p, const int* guard_mg = nullptr, const int* guard_eg = nullptr) {
     const u64 occ = occ_all(p), W = p.white, B = occ ^ p.white;
     int mg = 0, eg = 0;
     {
@@ -620,22 +646,11 @@ KB_HDN int static_eval(const Pos& p) {
     }
     const int wk = lsb(W & p.pc[KING]), bk = lsb(B & p.pc[KING]);
     const u64 wka = king_attacks(wk), bka = king_attacks(bk);
-    {
-        int v = guard_value(p, 27, occ) + guard_value(p, 28, occ) + guard_value(p, 35, occ) + guard_value(p, 36, occ);
-        mg += v * 20;
-        eg += v * 8;
-    }
-    for (u64 z = wka; z;) {
-        int g = guard_value(p, pop_lsb(z), occ);
-        if (g > 0) g = 0;
-        mg += g * 7;
-        eg += g * 6;
-    }
-    for (u64 z = bka; z;) {
-        int g = guard_value(p, pop_lsb(z), occ);
-        if (g < 0) g = 0;
-        mg += g * 7;
-        eg += g * 6;
+    if (guard_mg) {  // the caller (a warp) has already summed the guard terms below over its lanes
+        mg += *guard_mg;
+        eg += *guard_eg;
+    } else {
+        for (int i = 0; i < EVAL_GUARD_TERMS; ++i) eval_guard_term(p, i, mg, eg);
     }
     const u64 minors = p.pc[KNIGHT] | p.pc[BISHOP];
     const int dev = popc(minors & W & 0x000000FFFFFF0000ULL) + popc(minors & B & 0x0000FFFFFF000000ULL);

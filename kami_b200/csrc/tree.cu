@@ -350,7 +350,18 @@ __device__ void expand_once(const PoolDev& P, int t, const float* policy, float 
     const float leaf_turn = (depth & 1) ? -rt : rt;
     value = __fmul_rn(value, leaf_turn);  // (Q8) mcts.h:313
     if (!disable_bootstrap && P.cfg.bootstrap_weight > 0.0f) {
-        const float bs = bootstrap_value(c.leaf_pos, P.cfg.bootstrap_window);
+        // Env::bootstrap_value (env.h:476-484): the eval's 20 guard terms are spread over the lanes and summed
+        // (integer sums: same result in any order), the rest is cheap and uniform
+        int gm = 0, ge = 0;
+        if (lane < EVAL_GUARD_TERMS) eval_guard_term(c.leaf_pos, lane, gm, ge);
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            gm += __shfl_xor_sync(0xffffffffu, gm, off);
+            ge += __shfl_xor_sync(0xffffffffu, ge, off);
+        }
+        float bs = __fdiv_rn((float)static_eval(c.leaf_pos, &gm, &ge), P.cfg.bootstrap_window);
+        bs = bs < 1.0f ? bs : 1.0f;
+        bs = bs > -1.0f ? bs : -1.0f;
         const float a = __fmul_rn(__fsub_rn(1.0f, P.cfg.bootstrap_weight), value);
         const float b = __fmul_rn(__fmul_rn(P.cfg.bootstrap_weight, bs), P.cfg.bootstrap_amp);
         value = __fadd_rn(a, b);  // mcts.h:315-316
