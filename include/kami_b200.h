@@ -160,6 +160,10 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters);
 /* same, but every iteration's leaf planes round-trip through host memory like the reference
  * (H2D of obs + D2H of policy/value inside the call); used for the end-to-end bench figure */
 int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, float* policy_host, float* value_host);
+/* kb_pool_step_hostio serves the trees as `groups` independent pipelines, the analogue of the reference's
+ * inference_threads (selfplay.cpp:25-31): each group has its own NN::infer batch (so Q1's value indexing is per
+ * group) and its own streams, so one group's transfers overlap another's compute.  0 = default (4), max 8. */
+int kb_pool_set_hostio_groups(kb_pool* p, int groups);
 
 typedef struct kb_pool_stats {
     uint64_t evals;          /* NN evaluations (leaves expanded) */

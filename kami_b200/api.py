@@ -147,6 +147,7 @@ _SIGS = {
     "kb_pool_get_stats": (C.c_int, [_P, C.POINTER(PoolStats)]),
     "kb_pool_reset_stats": (C.c_int, [_P]),
     "kb_pool_set_policy_mode": (C.c_int, [_P, C.c_int]),
+    "kb_pool_set_hostio_groups": (C.c_int, [_P, C.c_int]),
     "kb_pool_drain_samples": (C.c_int, [_P, C.c_int, _f32p, _f32p, _f32p, _i32p]),
     "kb_pool_last_phase_ms": (C.c_int, [_P, C.POINTER(PhaseMs)]),
     "kb_pool_debug_select_profile": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int]),
@@ -494,6 +495,10 @@ class TreePool:
     def set_policy_mode(self, dense):
         """0: softmax over the legal moves only (default); 1: dense softmax over all 4672 actions."""
         _ck(self.L.kb_pool_set_policy_mode(self.h, int(dense)))
+
+    def set_hostio_groups(self, groups):
+        """step_hostio pipelines: groups of trees with their own NN::infer batch and streams (0 = default)."""
+        _ck(self.L.kb_pool_set_hostio_groups(self.h, int(groups)))
 
     def phase_ms(self):
         s = PhaseMs()

@@ -1459,13 +1459,15 @@ struct LegalRef {
     float* prior = nullptr;
 };
 
+// item0: first item of the activation workspace (X / Y / H) this forward may use, so that forwards of disjoint
+// groups of boards can run concurrently on different streams (kb_pool_step_hostio)
 static int net_forward_impl(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, const LegalRef& lr,
-                            cudaStream_t st) {
+                            cudaStream_t st, int item0 = 0) {
     if (!net->loaded) {
         set_error("network weights not loaded");
         return KB_ERR_STATE;
     }
-    int r = net_reserve(net, batch);
+    int r = net_reserve(net, batch + item0 * NB);
     if (r) return r;
     const uint4* in = reinterpret_cast<const uint4*>(planes);
     if (net->fused) {
@@ -1496,19 +1498,23 @@ static int net_forward_impl(kb_net* net, const void* planes, int batch, float* p
         if (net_stage_logits(net, batch, &logits)) return KB_ERR_CUDA;
     }
     size_t li = 0;
-    if ((r = run_conv(net->layers[li++], in, net->X, nullptr, nullptr, batch, st))) return r;
+    const int fs = (net->filters + 63) / 64;
+    uint4* X = net->X + (size_t)item0 * fs * SLAB_U4;
+    uint4* Y = net->Y + (size_t)item0 * fs * SLAB_U4;
+    uint4* H = net->H + (size_t)item0 * 2 * SLAB_U4;
+    if ((r = run_conv(net->layers[li++], in, X, nullptr, nullptr, batch, st))) return r;
     for (int i = 0; i < net->residuals; ++i) {
-        if ((r = run_conv(net->layers[li++], net->X, net->Y, nullptr, nullptr, batch, st))) return r;
-        if ((r = run_conv(net->layers[li++], net->Y, net->X, net->X, nullptr, batch, st))) return r;  // x = skip + relu(...)
+        if ((r = run_conv(net->layers[li++], X, Y, nullptr, nullptr, batch, st))) return r;
+        if ((r = run_conv(net->layers[li++], Y, X, X, nullptr, batch, st))) return r;  // x = skip + relu(...)
     }
-    if ((r = run_conv(net->layers[li++], net->X, net->H, nullptr, nullptr, batch, st))) return r;
-    if ((r = run_conv(net->layers[li++], net->H, nullptr, nullptr, logits, batch, st))) return r;
+    if ((r = run_conv(net->layers[li++], X, H, nullptr, nullptr, batch, st))) return r;
+    if ((r = run_conv(net->layers[li++], H, nullptr, nullptr, logits, batch, st))) return r;
     if (lr.act)
         k_legal_prior<<<(batch + 7) / 8, 256, 0, st>>>(logits, batch, lr.act, lr.nact, lr.stride, lr.prior, net->nan_flag);
     else
         k_softmax<<<batch, 256, 0, st>>>(logits, batch, net->nan_flag);
     KB_CUDA(cudaGetLastError());
-    k_value_head<<<batch, 256, 0, st>>>(net->X, (net->filters + 63) / 64, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, net->nan_flag);
+    k_value_head<<<batch, 256, 0, st>>>(X, fs, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, net->nan_flag);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
@@ -1516,6 +1522,14 @@ static int net_forward_impl(kb_net* net, const void* planes, int batch, float* p
 int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, cudaStream_t st) {
     return net_forward_impl(net, planes, batch, policy_dev, value256_dev, LegalRef{}, st);
 }
+
+// forward of one group of boards on the workspace starting at item0; planes = net_input_planes(net) + item0 items
+int net_forward_group_async(kb_net* net, int item0, int batch, float* policy_dev, float* value256_dev, cudaStream_t st) {
+    int r = net_reserve(net, batch + item0 * NB);
+    if (r) return r;
+    return net_forward_impl(net, net->P + (size_t)item0 * IN_SLABS * SLAB_U4, batch, policy_dev, value256_dev, LegalRef{}, st, item0);
+}
+void* net_group_planes(kb_net* net, int item0) { return net->P + (size_t)item0 * IN_SLABS * SLAB_U4; }
 
 int net_forward_legal_async(kb_net* net, const void* planes, int batch, const void* act_base, const void* nact_base, size_t stride,
                             float* prior_dev, float* value256_dev, cudaStream_t st) {

@@ -20,6 +20,11 @@ int net_reserve(kb_net* net, int batch);
 // input plane buffer owned by the net for `batch` boards (pad pixels already zero)
 void* net_input_planes(kb_net* net);
 int net_launches_per_forward(kb_net* net);
+// Group form: the forward of `batch` boards whose planes were written at net_group_planes(net, item0), using the
+// activation workspace from item `item0` on, so forwards of disjoint groups can run concurrently on different
+// streams.  Reserve the workspace for all groups (net_reserve) before the first group is launched.
+int net_forward_group_async(kb_net* net, int item0, int batch, float* policy_dev, float* value256_dev, cudaStream_t stream);
+void* net_group_planes(kb_net* net, int item0);
 // fp32 [n][64][30] observations -> bf16 tall-image planes (tree.cu)
 int obs_to_tall_launch(const float* obs_dev, int n, void* planes, cudaStream_t st);
 }  // namespace kb

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_reset(PoolDev P) 
 // few steps at a safe point: no leaf pending).  Same breadth-first order as the warp version, so
 // the resulting arena is identical; 256 parents per wave, children copied as one flat range.
 __global__ void __launch_bounds__(256) k_pool_compact(PoolDev P) {
-    const int t = blockIdx.x;
+    const int t = P.tree0 + blockIdx.x;
     TreeCtl& c = P.ctl[t];
     if (!c.want_compact) return;
     __shared__ u32 s_incl[256], s_oc[256], s_warp[8];
@@ -745,8 +746,8 @@ __global__ void __launch_bounds__(256) k_pool_compact(PoolDev P) {
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P, uint4* planes, Pos* leaf_out) {
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
     const int w = threadIdx.x >> 5;
-    const int t = blockIdx.x * WARPS_PER_BLOCK + w;
-    if (t >= P.n_trees) return;
+    const int t = P.tree0 + blockIdx.x * WARPS_PER_BLOCK + w;
+    if (t >= P.tree_hi) return;
     WarpScratch& s = scratch[w];
     TreeCtl& c = P.ctl[t];
     const bool prof = P.dbg != nullptr;
@@ -782,8 +783,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P,
                                                                       int compact) {
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
     const int w = threadIdx.x >> 5;
-    const int t = blockIdx.x * WARPS_PER_BLOCK + w;
-    if (t >= P.n_trees) return;
+    const int t = P.tree0 + blockIdx.x * WARPS_PER_BLOCK + w;
+    if (t >= P.tree_hi) return;
     if (*P.error) return;
     float v;
     if (!value_is_256) v = value[t];
@@ -1286,6 +1287,12 @@ int obs_to_tall_launch(const float* obs_dev, int n, void* planes, cudaStream_t s
 // ==========================================================================================
 // C ABI: tree pools
 // ==========================================================================================
+constexpr int HOSTIO_MAX_GROUPS = 8, HOSTIO_MAX_CHUNKS = 4;
+struct IoGroup {
+    cudaStream_t cs, d2h, h2d;
+    cudaEvent_t ev[4], evc[HOSTIO_MAX_CHUNKS];
+    unsigned selects;
+};
 struct kb_pool {
     PoolDev d;
     kb_tree_cfg cfg;
@@ -1306,8 +1313,9 @@ struct kb_pool {
     unsigned selects_since_compact;
     int policy_mode;  // kb_pool_step: 0 softmax over the legal moves only (default), 1 dense [n][4672] softmax
     cudaEvent_t ev[6];
-    cudaStream_t s_d2h, s_h2d;   // kb_pool_step_hostio: one copy stream per direction of the link
-    cudaEvent_t io_ev[12];
+    IoGroup io[HOSTIO_MAX_GROUPS];  // kb_pool_step_hostio: per group of trees a compute stream and a copy stream per direction
+    cudaEvent_t io_start;
+    int hostio_groups;  // 0 = default
     bool io_ready;
     cudaEvent_t evs[32][4];  // phase boundaries of up to 32 evenly spaced iterations of a kb_pool_step call
     bool evs_ready;
@@ -1381,6 +1389,8 @@ int kb_pool_create(kb_pool** out, int n_trees, int node_capacity, const kb_tree_
     p->cfg = *cfg;
     PoolDev& d = p->d;
     d.n_trees = n_trees;
+    d.tree0 = 0;
+    d.tree_hi = n_trees;
     d.cap = (u32)node_capacity;
     d.cfg = to_dev_cfg(*cfg);
     d.traj_cap = cfg->selfplay_nodes > 0 ? 640 : 1;
@@ -1429,9 +1439,14 @@ int kb_pool_destroy(kb_pool* p) {
     cudaFree(p->obs_batch_dev); cudaFree(d.dbg);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(p->ev[i]);
     if (p->io_ready) {
-        cudaStreamDestroy(p->s_d2h);
-        cudaStreamDestroy(p->s_h2d);
-        for (int i = 0; i < 12; ++i) cudaEventDestroy(p->io_ev[i]);
+        for (int g = 0; g < HOSTIO_MAX_GROUPS; ++g) {
+            cudaStreamDestroy(p->io[g].cs);
+            cudaStreamDestroy(p->io[g].d2h);
+            cudaStreamDestroy(p->io[g].h2d);
+            for (int i = 0; i < 4; ++i) cudaEventDestroy(p->io[g].ev[i]);
+            for (int i = 0; i < HOSTIO_MAX_CHUNKS; ++i) cudaEventDestroy(p->io[g].evc[i]);
+        }
+        cudaEventDestroy(p->io_start);
     }
     if (p->evs_ready)
         for (int i = 0; i < 32; ++i)
@@ -1698,57 +1713,129 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters) {
 // Reference-shaped data flow: every iteration's observations go to the host and come back, and so
 // do the policy / value rows (kami::NN::infer takes and returns host buffers, nn.cpp:155-187;
 // MCTS::expand takes a host policy row, mcts.h:257).  Buffers should be pinned.
+//
+// The trees are served as HOSTIO_GROUPS independent groups, each the analogue of one of the reference's inference
+// threads (selfplay.cpp:25-31: `inference_threads` loops, each with its own trees and its own NN::infer call on its
+// own batch -- so NN::infer's value indexing, Q1, applies per group).  A group is one chain
+//   select -> observe -> obs D2H -> obs H2D -> tower -> policy/value D2H -> policy/value H2D -> expand
+// on its own compute stream and its own copy stream per direction; the chains of different groups are independent,
+// so while one group computes or sends, another one receives: both directions of the link stay busy.
+static int hostio_env(const char* name, int def, int lo, int hi) {
+    const char* e = getenv(name);
+    int v = e ? atoi(e) : def;
+    return v < lo ? lo : v > hi ? hi : v;
+}
 int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, float* policy_host, float* value_host) {
     KB_ARG(p && net && iters > 0 && obs_host && policy_host && value_host, "pool/net/iters/buffers");
-    const size_t n = (size_t)p->d.n_trees;
+    const int n = p->d.n_trees;
     cudaStream_t st = main_stream();
-    if (!p->obs_batch_dev) KB_CUDA(cudaMalloc(&p->obs_batch_dev, sizeof(float) * KB_OBSIZE * n));
+    if (!p->obs_batch_dev) KB_CUDA(cudaMalloc(&p->obs_batch_dev, sizeof(float) * KB_OBSIZE * (size_t)n));
     if (!p->io_ready) {
-        KB_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
-        KB_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
-        for (int i = 0; i < 12; ++i) KB_CUDA(cudaEventCreateWithFlags(&p->io_ev[i], cudaEventDisableTiming));
+        for (int g = 0; g < HOSTIO_MAX_GROUPS; ++g) {
+            IoGroup& G = p->io[g];
+            KB_CUDA(cudaStreamCreateWithFlags(&G.cs, cudaStreamNonBlocking));
+            KB_CUDA(cudaStreamCreateWithFlags(&G.d2h, cudaStreamNonBlocking));
+            KB_CUDA(cudaStreamCreateWithFlags(&G.h2d, cudaStreamNonBlocking));
+            for (int i = 0; i < 4; ++i) KB_CUDA(cudaEventCreateWithFlags(&G.ev[i], cudaEventDisableTiming));
+            for (int i = 0; i < HOSTIO_MAX_CHUNKS; ++i) KB_CUDA(cudaEventCreateWithFlags(&G.evc[i], cudaEventDisableTiming));
+            G.selects = 0;
+        }
+        KB_CUDA(cudaEventCreateWithFlags(&p->io_start, cudaEventDisableTiming));
         p->io_ready = true;
     }
-    int r = net_reserve(net, (int)n);
+    int ngroups = p->hostio_groups > 0 ? p->hostio_groups : hostio_env("KB_HOSTIO_GROUPS", 4, 1, HOSTIO_MAX_GROUPS);
+    if (ngroups > n) ngroups = n;
+    const int per = (n + ngroups - 1) / ngroups;        // trees per group
+    const int items_per = items_for(per);               // workspace items per group (groups start on item boundaries)
+    int r = net_reserve(net, items_per * NB * ngroups);
     if (r) return r;
-    // Every array crosses the bus in both directions like in the reference (leaf observations out, NN::infer's host
-    // input in, its host policy / value out, MCTS::expand's host policy in).  The rows move in HOSTIO_CHUNKS pieces
-    // on a device->host and a host->device stream: piece c goes back up while piece c+1 is still coming down, so
-    // both directions of the link are busy at once; the data still passes through the caller's host buffers.
-    constexpr int HOSTIO_CHUNKS = 4;
-    cudaEvent_t ev_compute = p->io_ev[0], ev_back = p->io_ev[1];
-    cudaEvent_t* ev_piece = p->io_ev + 2;  // [HOSTIO_CHUNKS]
-    auto round_trip = [&](float* dev, float* host, size_t row_floats) -> int {
-        KB_CUDA(cudaEventRecord(ev_compute, st));
-        KB_CUDA(cudaStreamWaitEvent(p->s_d2h, ev_compute, 0));
-        for (int c = 0; c < HOSTIO_CHUNKS; ++c) {
-            const size_t r0 = n * c / HOSTIO_CHUNKS, r1 = n * (c + 1) / HOSTIO_CHUNKS;
+    KB_CUDA(cudaEventRecord(p->io_start, st));
+    for (int g = 0; g < ngroups; ++g) KB_CUDA(cudaStreamWaitEvent(p->io[g].cs, p->io_start, 0));
+    // dev -> host on the group's D2H stream once the compute stream got there, host -> dev behind it, compute resumes.
+    // The rows of array 0 move in `chunks` pieces so that piece c returns while piece c+1 is still leaving.
+    const int chunks = hostio_env("KB_HOSTIO_CHUNKS", 1, 1, HOSTIO_MAX_CHUNKS);
+    auto round_trip = [&](IoGroup& G, int rows, float* dev0, float* host0, size_t row_floats, float* dev1, float* host1, size_t bytes1) -> int {
+        KB_CUDA(cudaEventRecord(G.ev[0], G.cs));
+        KB_CUDA(cudaStreamWaitEvent(G.d2h, G.ev[0], 0));
+        if (bytes1) KB_CUDA(cudaMemcpyAsync(host1, dev1, bytes1, cudaMemcpyDeviceToHost, G.d2h));
+        for (int c = 0; c < chunks; ++c) {
+            const size_t r0 = (size_t)rows * c / chunks, r1 = (size_t)rows * (c + 1) / chunks;
             if (r1 == r0) continue;
             const size_t off = r0 * row_floats, bytes = (r1 - r0) * row_floats * sizeof(float);
-            KB_CUDA(cudaMemcpyAsync(host + off, dev + off, bytes, cudaMemcpyDeviceToHost, p->s_d2h));
-            KB_CUDA(cudaEventRecord(ev_piece[c], p->s_d2h));
-            KB_CUDA(cudaStreamWaitEvent(p->s_h2d, ev_piece[c], 0));
-            KB_CUDA(cudaMemcpyAsync(dev + off, host + off, bytes, cudaMemcpyHostToDevice, p->s_h2d));
+            KB_CUDA(cudaMemcpyAsync(host0 + off, dev0 + off, bytes, cudaMemcpyDeviceToHost, G.d2h));
+            KB_CUDA(cudaEventRecord(G.evc[c], G.d2h));
+            KB_CUDA(cudaStreamWaitEvent(G.h2d, G.evc[c], 0));
+            if (c == 0 && bytes1) KB_CUDA(cudaMemcpyAsync(dev1, host1, bytes1, cudaMemcpyHostToDevice, G.h2d));
+            KB_CUDA(cudaMemcpyAsync(dev0 + off, host0 + off, bytes, cudaMemcpyHostToDevice, G.h2d));
         }
-        KB_CUDA(cudaEventRecord(ev_back, p->s_h2d));
-        KB_CUDA(cudaStreamWaitEvent(st, ev_back, 0));
+        KB_CUDA(cudaEventRecord(G.ev[2], G.h2d));
+        KB_CUDA(cudaStreamWaitEvent(G.cs, G.ev[2], 0));
         return KB_OK;
     };
+    const bool dbg = getenv("KB_HOSTIO_DEBUG") != nullptr;
+    const auto host_t0 = std::chrono::steady_clock::now();
     for (int it = 0; it < iters; ++it) {
-        // select + Env::observe on the device; observations out to the caller's buffer and back in as NN::infer's input
-        if ((r = pool_launch_select(p, nullptr, p->leaf_dev, st))) return r;
-        if ((r = kb_encode_planes_dev((const kb_position*)p->leaf_dev, (int)n, p->obs_batch_dev))) return r;
-        if ((r = round_trip(p->obs_batch_dev, obs_host, KB_OBSIZE))) return r;
-        if ((r = obs_to_tall_launch(p->obs_batch_dev, (int)n, net_input_planes(net), st))) return r;
-        if ((r = net_forward_async(net, net_input_planes(net), (int)n, p->policy_dev, p->value_dev, st))) return r;
-        // NN::infer's host policy / value out (value[i] = vh.flat[i], Q1), MCTS::expand's host policy row / value in
-        if ((r = round_trip(p->value_dev, value_host, 1))) return r;
-        if ((r = round_trip(p->policy_dev, policy_host, KB_PSIZE))) return r;
-        k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 0, 0, 0);
-        KB_CUDA(cudaGetLastError());
-        p->launches += 4 + (unsigned long long)net_launches_per_forward(net);
+        for (int g = 0; g < ngroups; ++g) {
+            IoGroup& G = p->io[g];
+            const int t0 = g * per, t1 = (g + 1) * per < n ? (g + 1) * per : n, m = t1 - t0;
+            if (m <= 0) continue;
+            PoolDev d = p->d;
+            d.tree0 = t0;
+            d.tree_hi = t1;
+            d.defer_compact = 1;
+            const int blocks = (m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+            if (G.selects++ % COMPACT_PERIOD == 0) {
+                k_pool_compact<<<m, 256, 0, G.cs>>>(d);
+                p->launches++;
+            }
+            // select + Env::observe on the device; observations out to the caller's buffer and back in as NN::infer's input
+            k_pool_select<<<blocks, 32 * WARPS_PER_BLOCK, 0, G.cs>>>(d, nullptr, p->leaf_dev);
+            float* obs_dev = p->obs_batch_dev + (size_t)t0 * KB_OBSIZE;
+            k_encode_f32<<<(m + 3) / 4, 128, 0, G.cs>>>(p->leaf_dev + t0, m, obs_dev);
+            KB_CUDA(cudaGetLastError());
+            if ((r = round_trip(G, m, obs_dev, obs_host + (size_t)t0 * KB_OBSIZE, KB_OBSIZE, nullptr, nullptr, 0))) return r;
+            const int item0 = g * items_per;
+            if ((r = obs_to_tall_launch(obs_dev, m, net_group_planes(net, item0), G.cs))) return r;
+            float* pol_dev = p->policy_dev + (size_t)t0 * KB_PSIZE;
+            float* val_dev = p->value_dev + (size_t)t0 * KB_VALUE_WIDTH;  // [m][256]; NN::infer hands out its first m floats (Q1)
+            if ((r = net_forward_group_async(net, item0, m, pol_dev, val_dev, G.cs))) return r;
+            // NN::infer's host policy / value out, MCTS::expand's host policy row / value in
+            const bool fixed_value = p->d.cfg.value_index_mode == 1;  // opt-in: value[i] = vh[i][0] instead of vh.flat[i]
+            if (fixed_value) {  // strided gather of column 0 through the caller's value array and back
+                KB_CUDA(cudaEventRecord(G.ev[0], G.cs));
+                KB_CUDA(cudaStreamWaitEvent(G.d2h, G.ev[0], 0));
+                KB_CUDA(cudaMemcpy2DAsync(value_host + t0, sizeof(float), val_dev, sizeof(float) * KB_VALUE_WIDTH, sizeof(float), (size_t)m,
+                                          cudaMemcpyDeviceToHost, G.d2h));
+                KB_CUDA(cudaMemcpy2DAsync(val_dev, sizeof(float) * KB_VALUE_WIDTH, value_host + t0, sizeof(float), sizeof(float), (size_t)m,
+                                          cudaMemcpyHostToDevice, G.d2h));
+                KB_CUDA(cudaEventRecord(G.ev[2], G.d2h));
+                KB_CUDA(cudaStreamWaitEvent(G.cs, G.ev[2], 0));
+                if ((r = round_trip(G, m, pol_dev, policy_host + (size_t)t0 * KB_PSIZE, KB_PSIZE, nullptr, nullptr, 0))) return r;
+                k_pool_expand<<<blocks, 32 * WARPS_PER_BLOCK, 0, G.cs>>>(d, p->policy_dev, p->value_dev, 1, 0, 0);
+            } else {
+                if ((r = round_trip(G, m, pol_dev, policy_host + (size_t)t0 * KB_PSIZE, KB_PSIZE, val_dev, value_host + t0, sizeof(float) * (size_t)m)))
+                    return r;
+                // value[t] of the kernel = the group's flat value row (nn.cpp:186): val_dev[t - t0]
+                k_pool_expand<<<blocks, 32 * WARPS_PER_BLOCK, 0, G.cs>>>(d, p->policy_dev, val_dev - t0, 0, 0, 0);
+            }
+            KB_CUDA(cudaGetLastError());
+            p->launches += 4 + (unsigned long long)net_launches_per_forward(net);
+        }
+    }
+    if (dbg)
+        fprintf(stderr, "[kb hostio] %d groups x %d chunks: host enqueue %.3f ms for %d iterations\n", ngroups, chunks,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(), iters);
+    for (int g = 0; g < ngroups; ++g) {
+        KB_CUDA(cudaEventRecord(p->io[g].ev[3], p->io[g].cs));
+        KB_CUDA(cudaStreamWaitEvent(st, p->io[g].ev[3], 0));
     }
     return pool_check(p, true);
+}
+
+int kb_pool_set_hostio_groups(kb_pool* p, int groups) {
+    KB_ARG(p && groups >= 0 && groups <= HOSTIO_MAX_GROUPS, "pool/groups");
+    p->hostio_groups = groups;
+    return KB_OK;
 }
 
 int kb_pool_get_stats(kb_pool* p, kb_pool_stats* out) {

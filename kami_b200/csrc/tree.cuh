@@ -84,6 +84,8 @@ struct Stats {
 
 struct PoolDev {
     int n_trees;
+    int tree0, tree_hi;  // the range of trees a batched launch serves (whole pool: 0, n_trees); kb_pool_step_hostio runs
+                         // groups of trees as independent pipelines on their own streams
     u32 cap;  // nodes per semi-space per tree
     Node* nodes;
     u32* meta;

@@ -406,24 +406,52 @@ def test_pool_step_selfplay_smoke(kb):
             assert abs(float(p.sum()) - 1.0) < 1e-3
 
 
-def test_pool_step_matches_hostio_path(kb):
+@pytest.mark.parametrize("F,R,groups,vmode", [(64, 1, 1, 0), (64, 1, 4, 1), (64, 1, 3, 1), (128, 1, 4, 1)])
+def test_pool_step_matches_hostio_path(kb, F, R, groups, vmode):
     """kb_pool_step (resident) and kb_pool_step_hostio (reference-shaped host round trip) drive
-    identical searches when noise is off."""
-    F, R, n = 64, 1, 32
+    identical searches when noise is off.  One group = one NN::infer batch over all trees, so the reference's
+    value indexing (Q1, value[i] = vh.flat[i]) matches the resident step; with several pipelined groups each
+    group is its own NN::infer batch, which is the same search only under value_index_mode 1 (vh[i][0])."""
+    n = 32 if groups != 3 else 31  # ragged last group
     params = NO.init_params(F, R, seed=4)
     net = kb.NN(F, R)
     net.load_blob(NO.pack_blob(params, F, R))
-    kw = dict(noise_weight=0.0, selfplay_nodes=16, seed=1, **H.DEF_YML)
+    kw = dict(noise_weight=0.0, selfplay_nodes=16, seed=1, value_index_mode=vmode, **H.DEF_YML)
     a, b = kb.TreePool(n, 1 << 14, _cfg(kb, **kw)), kb.TreePool(n, 1 << 14, _cfg(kb, **kw))
     a.set_policy_mode(1)  # dense softmax, the arithmetic of the host round trip
     a.step(net, 60)
     obs = np.zeros((n, 1920), np.float32)
     pol = np.zeros((n, H.PSIZE), np.float32)
     val = np.zeros(n, np.float32)
+    b.set_hostio_groups(groups)
     b.step_hostio(net, 60, obs, pol, val)
-    for i in (0, 5, n - 1):
+    for i in range(n):
         assert a.tree(i).digest() == b.tree(i).digest()
     assert a.stats()["moves"] == b.stats()["moves"]
+    # the caller's buffers hold the last iteration's rows: every policy row is a distribution over 4672 actions
+    assert np.allclose(pol.sum(1), 1.0, atol=1e-3) and np.isfinite(val).all() and (np.abs(obs).sum(1) > 0).all()
+
+
+def test_hostio_groups_reproduce_per_thread_value_indexing(kb):
+    """Reference mode (Q1): with G groups, tree t of group g is expanded with vh.flat[t - t0(g)] of the GROUP's batch,
+    exactly what inference thread g of the reference sees from its own NN::infer call (nn.cpp:186).  Checked by
+    running group g's trees alone in a pool of their own with the same per-tree seeds (noise off, argmax picks)."""
+    F, R, n, G = 64, 1, 16, 2
+    params = NO.init_params(F, R, seed=5)
+    net = kb.NN(F, R)
+    net.load_blob(NO.pack_blob(params, F, R))
+    kw = dict(noise_weight=0.0, selfplay_nodes=12, seed=3, alpha_initial=0.0, alpha_final=0.0, **H.DEF_YML)
+    obs = np.zeros((n, 1920), np.float32)
+    pol = np.zeros((n, H.PSIZE), np.float32)
+    val = np.zeros(n, np.float32)
+    whole = kb.TreePool(n, 1 << 14, _cfg(kb, **kw))
+    whole.set_hostio_groups(G)
+    whole.step_hostio(net, 40, obs, pol, val)
+    first = kb.TreePool(n // G, 1 << 14, _cfg(kb, **kw))  # trees 0..7 = group 0 (same tree ids, same seeds)
+    first.set_hostio_groups(1)
+    first.step_hostio(net, 40, obs, pol, val)
+    for i in range(n // G):
+        assert whole.tree(i).digest() == first.tree(i).digest()
 
 
 @pytest.mark.parametrize("F,R", [(64, 2), (128, 1)])
