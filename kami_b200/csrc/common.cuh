@@ -23,6 +23,31 @@ bool initialized();
         }                                                                                         \
     } while (0)
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl may become resident while the kernel before
+// it on the stream is still running, run its own set-up (barrier init, TMEM allocation, zero fills, constant loads)
+// and must execute pdl_wait() before it touches anything the earlier kernel writes or reads.  Every kernel of such a
+// chain calls pdl_wait() unconditionally, so "my predecessor completed" also means all earlier kernels completed.
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int pdl_mask();  // KB_PDL_MASK: bit 0 select, bit 1 tower, bit 2 expand launched with the PDL attribute (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_mask() >> which) & 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define KB_REQUIRE_INIT()                                                    \
     do {                                                                     \
         if (!kb::initialized()) {                                            \

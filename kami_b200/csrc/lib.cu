@@ -1,4 +1,5 @@
 // Library-level plumbing of libkami_b200: device binding, error strings, raw memory helpers.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -19,6 +20,14 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 cudaStream_t main_stream() { return g_stream; }
+int pdl_mask() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("KB_PDL_MASK");
+        m = e ? atoi(e) & 7 : 3;  // select + tower; expand launched plainly (measured: PDL on expand costs 8-10 us per step)
+    }
+    return m;
+}
 int sm_count() { return g_sms; }
 bool initialized() { return g_init; }
 int upload_tables();  // tree.cu

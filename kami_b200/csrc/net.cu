@@ -799,12 +799,18 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
     const uint32_t p_full = s0 + 8u * 16, t_full = s0 + 8u * 17, act_ready = s0 + 8u * 18, region_clean = s0 + 8u * 19;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
     float* vbuf = reinterpret_cast<float*>(smem + 512);     // [7][64] value-conv outputs
-    float* sbias = reinterpret_cast<float*>(smem + 2560);   // all folded biases
+    float* sbias = reinterpret_cast<float*>(smem + 2560);   // all folded biases (n_bias <= 1400 floats)
+    float* sred = reinterpret_cast<float*>(smem + 2304);    // [8][7] block-reduction scratch of the dense softmax (224 B)
     uint8_t* region = smem + FZ_HDR;
     const uint32_t region_s = s0 + FZ_HDR;
     const uint32_t ring_s = region_s + FZ_REGION;
 
     const int my_items = P.items > (int)blockIdx.x ? (P.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // PDL: this CTA may have become resident while the kernel before it on the stream (the pool's select) is still
+    // draining.  Everything up to each role's pdl_wait() touches only this CTA's shared / tensor memory and constant
+    // weights; planes, legal-action lists and the output rows are only touched after it.  Each role triggers the
+    // dependents when its last item is nearly done.  (The pool's expand is launched without the PDL attribute by default:
+    // letting it in early was measured 8-10 us per step slower whether triggered here or at the top; KB_PDL_MASK.)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < FZ_NSTAGE; ++s) {
@@ -833,6 +839,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             ptx::mbar_wait(region_clean, ii & 1);
+            if (ii == 0) pdl_wait();
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(p_full, SLAB_BYTES);
                 ptx::bulk_g2s(region_s + SLAB_BYTES, P.planes + (size_t)item * IN_SLABS * SLAB_U4, SLAB_BYTES, p_full);
@@ -858,10 +865,12 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 }
             }
         }
+        pdl_launch_dependents();
     } else if (warp == 1) {
         // ===== MMA issuer (converged warp, one elected lane issues) =====
         int stage = 0, sphase = 0;
         uint32_t act_phase = 0;
+        pdl_wait();
         for (int ii = 0; ii < my_items; ++ii) {
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
@@ -913,9 +922,63 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 if (ptx::elect_one()) ptx::mma_commit(t_full);
                 __syncwarp();
             }
+            if (ii + 1 == my_items) pdl_launch_dependents();
             // the last layer's epilogue also signals act_ready (TMEM drained) -- consume it
             ptx::mbar_wait(act_ready, act_phase);
             act_phase ^= 1;
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===== value head, second half: Linear(64 -> 256) + tanh (nn.cpp:87-88) on the value conv's outputs, off the
+        // epilogue warps' critical path (they go on with the policy head meanwhile).  Thread j owns outputs 4j..4j+3. =====
+        const int j = threadIdx.x - 64;  // 0..63
+        pdl_wait();
+        for (int ii = 0; ii < my_items; ++ii) {
+            const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.fcb) + j);
+            float o[NB][4];
+#pragma unroll
+            for (int s = 0; s < NB; ++s) { o[s][0] = b4.x; o[s][1] = b4.y; o[s][2] = b4.z; o[s][3] = b4.w; }
+            const float4* wt = reinterpret_cast<const float4*>(P.fct) + j;  // fct[p][256]
+            float4 wq[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) wq[p] = __ldg(wt + p * 64);  // first quarter of the weights in flight before the wait
+            asm volatile("bar.sync 2, 320;" ::: "memory");
+#pragma unroll
+            for (int pq = 0; pq < 4; ++pq) {
+                float4 wn[16];
+                if (pq < 3) {
+#pragma unroll
+                    for (int p = 0; p < 16; ++p) wn[p] = __ldg(wt + ((pq + 1) * 16 + p) * 64);
+                }
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+#pragma unroll
+                    for (int s = 0; s < NB; ++s) {
+                        const float v = vbuf[s * 64 + pq * 16 + p];
+                        o[s][0] = fmaf(v, wq[p].x, o[s][0]);
+                        o[s][1] = fmaf(v, wq[p].y, o[s][1]);
+                        o[s][2] = fmaf(v, wq[p].z, o[s][2]);
+                        o[s][3] = fmaf(v, wq[p].w, o[s][3]);
+                    }
+                }
+                if (pq < 3) {
+#pragma unroll
+                    for (int p = 0; p < 16; ++p) wq[p] = wn[p];
+                }
+            }
+            if (ii + 1 < my_items) asm volatile("bar.arrive 3, 320;" ::: "memory");  // vbuf may be overwritten
+            else pdl_launch_dependents();
+            bool bad = false;
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                const int board = item * NB + s;
+                if (board < P.boards) {
+                    const float4 t = make_float4(tanhf(o[s][0]), tanhf(o[s][1]), tanhf(o[s][2]), tanhf(o[s][3]));
+                    bad |= (t.x != t.x) | (t.y != t.y) | (t.z != t.z) | (t.w != t.w);
+                    reinterpret_cast<float4*>(P.value256 + (size_t)board * 256)[j] = t;
+                }
+            }
+            if (bad) atomicExch(P.nan_flag, 1);
         }
     } else if (warp >= 4) {
         // ===== epilogue warps =====
@@ -936,6 +999,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(region_clean);
             }
+            if (ii == 0) pdl_wait();
             KB_STAMP();
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
@@ -1016,8 +1080,9 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 if (lane == 0) ptx::mbar_arrive(act_ready);
                 KB_STAMP();
                 if (l == P.tower_layers - 1) {
-                    // ---- value head on X (nn.cpp:83-88), overlapping the policy conv's MMAs ----
+                    // ---- value conv 1x1 + ReLU on X (nn.cpp:83-86); the 64 -> 256 Linear + tanh runs on warps 2-3 ----
                     epi_bar();  // X complete
+                    if (ii > 0) asm volatile("bar.sync 3, 320;" ::: "memory");  // vbuf consumed by the previous item's Linear
                     const uint4* X = reinterpret_cast<const uint4*>(region + P.layer[l].dst_off);
                     for (int i = et; i < NB * 64; i += FZ_EPI_THREADS) {
                         const int slot = i >> 6, pix = i & 63;
@@ -1036,30 +1101,12 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                         }
                         vbuf[i] = fmaxf(acc, 0.0f);
                     }
-                    epi_bar();
-                    float o[NB];
-                    const float b0 = __ldg(P.fcb + et);
-#pragma unroll
-                    for (int s = 0; s < NB; ++s) o[s] = b0;
-#pragma unroll 4
-                    for (int p = 0; p < 64; ++p) {
-                        const float wgt = __ldg(P.fct + p * 256 + et);
-#pragma unroll
-                        for (int s = 0; s < NB; ++s) o[s] = fmaf(vbuf[s * 64 + p], wgt, o[s]);
-                    }
-#pragma unroll
-                    for (int s = 0; s < NB; ++s) {
-                        const int board = item * NB + s;
-                        if (board < P.boards) {
-                            const float t = tanhf(o[s]);
-                            if (t != t) atomicExch(P.nan_flag, 1);
-                            P.value256[(size_t)board * 256 + et] = t;
-                        }
-                    }
+                    asm volatile("bar.arrive 2, 320;" ::: "memory");  // vbuf ready for warps 2-3
                 }
             }
             // ---- softmax over the 4672 logits of each board (nn.cpp:80) ----
             epi_bar();
+            if (ii + 1 == my_items) pdl_launch_dependents();
             KB_STAMP();
             if (P.legal_act) {
                 // ---- softmax numerators over the legal moves only: warp e gathers board e's logits ----
@@ -1091,7 +1138,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 }
             } else {
                 // every thread owns 19 logits of each of the 7 boards; two block-wide reductions in total
-                float* red = vbuf;  // [8 warps][7] maxima, then [8][7] sums (the value head is done with vbuf)
+                float* red = sred;  // [8 warps][7] maxima, then [8][7] sums
                 const float* lg = reinterpret_cast<const float*>(region);
                 constexpr int PER = (KB_PSIZE + FZ_EPI_THREADS - 1) / FZ_EPI_THREADS;  // 19
                 float m[NB], sum[NB];
@@ -1489,8 +1536,7 @@ static int net_forward_impl(kb_net* net, const void* planes, int batch, float* p
         fp.items = items_for(batch);
         fp.boards = batch;
         const int grid = fp.items < sm_count() ? fp.items : sm_count();
-        k_tower64<<<grid, 384, FZ_SMEM, st>>>(fp);
-        KB_CUDA(cudaGetLastError());
+        KB_CUDA(launch_pdl(1, k_tower64, dim3(grid), dim3(384), FZ_SMEM, st, fp));
         return KB_OK;
     }
     float* logits = policy_dev;

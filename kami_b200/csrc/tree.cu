@@ -747,6 +747,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P,
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
     const int w = threadIdx.x >> 5;
     const int t = P.tree0 + blockIdx.x * WARPS_PER_BLOCK + w;
+    pdl_launch_dependents();  // the tower's CTAs may move in (and set up) as this grid's blocks drain
+    pdl_wait();
     if (t >= P.tree_hi) return;
     WarpScratch& s = scratch[w];
     TreeCtl& c = P.ctl[t];
@@ -784,6 +786,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P,
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
     const int w = threadIdx.x >> 5;
     const int t = P.tree0 + blockIdx.x * WARPS_PER_BLOCK + w;
+    pdl_launch_dependents();
+    pdl_wait();
     if (t >= P.tree_hi) return;
     if (*P.error) return;
     float v;
@@ -1622,8 +1626,7 @@ static int pool_launch_select(kb_pool* p, uint4* planes, Pos* leaf_out, cudaStre
         KB_CUDA(cudaGetLastError());
         p->launches++;
     }
-    k_pool_select<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(d, planes, leaf_out);
-    KB_CUDA(cudaGetLastError());
+    KB_CUDA(launch_pdl(0, k_pool_select, dim3(pool_blocks(p)), dim3(32 * WARPS_PER_BLOCK), 0, st, d, planes, leaf_out));
     return KB_OK;
 }
 
@@ -1686,8 +1689,8 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters) {
             r = net_forward_async(net, planes, n, p->policy_dev, p->value_dev, st);
         if (r) return r;
         if (timed) KB_CUDA(cudaEventRecord(p->evs[k][2], st));
-        k_pool_expand<<<pool_blocks(p), 32 * WARPS_PER_BLOCK, 0, st>>>(p->d, p->policy_dev, p->value_dev, 1, 0, legal ? 1 : 0);
-        KB_CUDA(cudaGetLastError());
+        KB_CUDA(launch_pdl(2, k_pool_expand, dim3(pool_blocks(p)), dim3(32 * WARPS_PER_BLOCK), 0, st, p->d, (const float*)p->policy_dev,
+                           (const float*)p->value_dev, 1, 0, legal ? 1 : 0));
         if (timed) KB_CUDA(cudaEventRecord(p->evs[k][3], st));
         p->launches += 2 + (unsigned long long)net_launches_per_forward(net);
     }
