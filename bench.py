@@ -377,6 +377,37 @@ def bind_to_gpu_numa(local):
         return "not bound (%s)" % type(e).__name__
 
 
+def encoder_leg(api, L, pool, hbm_peak, peak_kind, n=131072, reps=10):
+    """north_star kernel 1 on its own (encoder roofline): n mid-game positions (the pool's current leaves,
+    tiled) -> input planes, positions and planes resident in HBM.  Algorithmic bytes per position: 64 B of position
+    read + the planes written -- 7 680 B as fp32 [64][30] (Env::observe's layout), 4 096 B as the tower's bf16 input
+    (30 channels padded to 32).  The 1 GB / 1.5 GB outputs are larger than L2, no flush needed."""
+    leaves = pool.leaf_positions()
+    pos = np.tile(leaves, (n + len(leaves) - 1) // len(leaves))[:n].copy()
+    dpos, dobs, dtall = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    api._ck(L.kb_dev_alloc(C.byref(dpos), pos.nbytes))
+    api._ck(L.kb_dev_alloc(C.byref(dobs), n * 1920 * 4))
+    api._ck(L.kb_dev_alloc(C.byref(dtall), L.kb_net_planes_bytes(n)))
+    api._ck(L.kb_dev_upload(dpos, pos.ctypes.data_as(C.c_void_p), pos.nbytes))
+    out = {"positions": n, "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_kind": peak_kind}
+    ms = C.c_float()
+    for name, fn, nbytes in (("k_encode_f32", lambda: L.kb_encode_planes_dev(dpos, n, dobs), 64 + 7680),
+                             ("k_encode_tall", lambda: L.kb_encode_planes_bf16_dev(dpos, n, dtall), 64 + 4096)):
+        for _ in range(3):
+            api._ck(fn())
+        L.kb_dev_sync()
+        L.kb_timer_start()
+        for _ in range(reps):
+            api._ck(fn())
+        L.kb_timer_stop(C.byref(ms))
+        t = ms.value * 1e-3 / reps
+        out[name] = {"us_per_launch": t * 1e6, "positions_per_sec": n / t, "algorithmic_bytes_per_position": nbytes,
+                     "achieved": n * nbytes / t / 1e9, "frac": n * nbytes / t / 1e9 / hbm_peak}
+    for p in (dpos, dobs, dtall):
+        L.kb_dev_free(p)
+    return out
+
+
 def run_ours(args, rank, world, local, dist):
     numa = bind_to_gpu_numa(local)
     import kami_b200
@@ -493,6 +524,10 @@ def run_ours(args, rank, world, local, dist):
             del big
         except Exception as e:  # never lose the bench line to the extra measurement
             extras["tower_20x256"] = {"error": str(e)}
+        try:
+            extras["roofline_encoder"] = encoder_leg(api, L, pool, hbm_peak, peak_kind)
+        except Exception as e:
+            extras["roofline_encoder"] = {"error": str(e)}
         if world == 1:
             ev, mv, dt, kind = reference_loop(12.0, 3, 16)
             cores = os.cpu_count() or 1

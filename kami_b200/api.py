@@ -290,6 +290,27 @@ def encode_planes(positions):
     return out
 
 
+def encode_planes_tall(positions):
+    """The tower's own input: bf16 planes in the swizzled tall-image layout (csrc/layout.cuh), as raw uint16 of shape
+    [items][640 pixels][64 channels-in-swizzled-order]; device encoder kb_encode_planes_bf16_dev."""
+    p = as_positions(positions)
+    L = lib()
+    nbytes = L.kb_net_planes_bytes(len(p))
+    dpos, dpl = _P(), _P()
+    _ck(L.kb_dev_alloc(C.byref(dpos), max(16, p.nbytes)))
+    _ck(L.kb_dev_alloc(C.byref(dpl), nbytes))
+    try:
+        _ck(L.kb_dev_upload(dpos, _vp(p), p.nbytes))
+        _ck(L.kb_encode_planes_bf16_dev(dpos, len(p), dpl))
+        out = np.zeros(nbytes // 2, np.uint16)
+        _ck(L.kb_dev_download(_vp(out), dpl, nbytes))
+    finally:
+        L.kb_dev_free(dpos)
+        L.kb_dev_free(dpl)
+    items = (len(p) + 6) // 7
+    return out[: items * 640 * 64].reshape(items, 640, 64), out[items * 640 * 64:]
+
+
 def legal_actions(positions):
     p = as_positions(positions)
     acts = np.zeros((len(p), MAX_ACTIONS), np.int32)

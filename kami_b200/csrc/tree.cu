@@ -87,41 +87,96 @@ __device__ int warp_legal_actions(const Pos& p, WarpScratch& s, u16* out) {
     return base;
 }
 
-// env.h:202-262 as fp32 [64][30], the API-compat layout.  Coalesced: the warp walks the 1920
-// floats of the position in order.
-__device__ void warp_encode_f32(const Pos& p, float* dst) {
-    const int lane = lane_id();
-    for (int e = lane; e < 64 * NFEATURES; e += 32) {
-        const int q = e / NFEATURES, f = e - q * NFEATURES;
-        dst[e] = plane_value(p, q, f);
-    }
+// ---- plane encoders (north_star kernel 1; Env::observe, env.h:202-262) ----------------------------------------------
+// A position's 30 features per square are an 18-feature header that is the same on all 64 squares (ply bits 0-7, Q13;
+// halfmove-clock bits 0-5; the four castle slots holding RAW mask values 1/2/4/8, Q2) and a one-hot over 12 piece
+// planes at the POV-rotated square.  Both encoders build the header once per position and look up each square's
+// hot feature once, then only assemble 16-byte vectors.
+
+// hot feature (18..29) of POV square q, or -1 for an empty square
+__device__ __forceinline__ int hot_feature(const Pos& p, int q) {
+    const int sq = p.ctm == BLACK ? 63 - q : q;
+    const int t = type_at(p, sq);
+    return t < 0 ? -1 : 18 + (color_at(p, sq) != p.ctm ? 6 : 0) + t;
 }
-// bf16 planes in the swizzled tall-image layout the conv tower consumes (layout.cuh): the 30
-// features fill channels 0..29 of the input slab (chunks 0..3 of each pixel line).
+// value of castle slot f (14..17) as the raw mask the reference stores (env.h:219-235)
+__device__ __forceinline__ int castle_slot(const Pos& p, int f) {
+    const int wm = 1 << (f - 14);
+    const int m = p.ctm == WHITE ? wm : (wm < 4 ? wm << 2 : wm >> 2);
+    return p.castle & m;
+}
+// bf16 bit pattern of v in {0, 1, 2, 4, 8}
+__device__ __forceinline__ u32 bf16_pow2(int v) { return v ? 0x3F80u + ((u32)(31 - __clz(v)) << 7) : 0u; }
+
+// fp32 [64][30], the API-compat layout (7 680 B per position): the warp writes the position's 480 float4 in order,
+// 15 per lane, fully coalesced.  hdr / hot: 18 floats and 64 bytes of per-warp shared scratch.
+__device__ void warp_encode_f32(const Pos& p, float* dst, float* hdr, signed char* hot) {
+    const int lane = lane_id();
+    if (lane < 18) {
+        const int f = lane;
+        hdr[f] = f < 8 ? (float)((p.ply >> f) & 1) : f < 14 ? (float)((p.hmc >> (f - 8)) & 1) : (float)castle_slot(p, f);
+    }
+    hot[lane] = (signed char)hot_feature(p, lane);
+    hot[lane + 32] = (signed char)hot_feature(p, lane + 32);
+    __syncwarp();
+    float4* out = reinterpret_cast<float4*>(dst);
+#pragma unroll 5
+    for (int j = 0; j < 15; ++j) {
+        const int v = lane + 32 * j;
+        int q = (4 * v) / NFEATURES, f = 4 * v - q * NFEATURES;
+        float e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            e[i] = f < 18 ? hdr[f] : (hot[q] == f ? 1.0f : 0.0f);
+            if (++f == NFEATURES) {
+                f = 0;
+                ++q;
+            }
+        }
+        out[v] = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    __syncwarp();
+}
+// bf16 planes in the swizzled tall-image layout the conv tower consumes (layout.cuh): the 30 features fill channels
+// 0..29 of the input slab = chunks 0..3 (64 B) of each pixel line.  Chunks 0-1 (features 0..15) and the first word of
+// chunk 2 (features 16, 17) are header-only; the rest is the one-hot.  Four lanes serve one pixel, lane & 3 = chunk:
+// the swizzle (slot = chunk ^ (pixel & 7)) keeps chunks {0,1} and {2,3} in one aligned 32-byte sector each, so a warp
+// store writes 16 whole sectors (8 pixels x 64 B) instead of 32 half sectors.
 __device__ void warp_encode_tall(const Pos& p, int board, uint4* planes) {
     const int lane = lane_id();
     const int item = board / NB, slot = board - item * NB;
     uint4* base = planes + (size_t)item * IN_SLABS * SLAB_U4;
+    const int c = lane & 3;
+    // hot features of squares lane and lane + 32; pixel q's value is fetched from lane q & 31
+    const int hot_lo = hot_feature(p, lane), hot_hi = hot_feature(p, lane + 32);
+    uint4 hdr = make_uint4(0u, 0u, 0u, 0u);  // this lane's header words: chunk 0 / 1 entirely, word 0 of chunk 2
+    if (c < 2) {
+        const u32 bits = ((u32)(p.ply & 0xFF) | ((u32)(p.hmc & 0x3F) << 8)) >> (8 * c);
+        u32 w[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int q = lane + 32 * h;
+        for (int k = 0; k < 4; ++k) w[k] = ((bits >> (2 * k)) & 1u) * 0x3F80u | ((bits >> (2 * k + 1)) & 1u) * 0x3F800000u;
+        if (c == 1) w[3] = bf16_pow2(castle_slot(p, 14)) | (bf16_pow2(castle_slot(p, 15)) << 16);
+        hdr = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if (c == 2) {
+        hdr.x = bf16_pow2(castle_slot(p, 16)) | (bf16_pow2(castle_slot(p, 17)) << 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int q = (lane >> 2) + 8 * j;
+        const int lo = __shfl_sync(0xffffffffu, hot_lo, q & 31), hi = __shfl_sync(0xffffffffu, hot_hi, q & 31);
+        const int hot = j < 4 ? lo : hi;
         const int px = tall_pixel(slot, q);
-        const int sq = p.ctm == BLACK ? 63 - q : q;
-        const int t = type_at(p, sq);
-        const int hot = t < 0 ? -1 : 18 + (color_at(p, sq) != p.ctm ? 6 : 0) + t;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            u32 w[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int f0 = c * 8 + 2 * k, f1 = f0 + 1;
-                const float v0 = f0 < 18 ? header_feature(p, f0) : (f0 == hot ? 1.0f : 0.0f);
-                const float v1 = f1 < 18 ? header_feature(p, f1) : (f1 == hot ? 1.0f : 0.0f);
-                const __nv_bfloat162 b = __floats2bfloat162_rn(v0, v1);
-                w[k] = *reinterpret_cast<const u32*>(&b);
-            }
-            base[chunk_u4(px, c)] = make_uint4(w[0], w[1], w[2], w[3]);
+        uint4 v = hdr;
+        if (c >= 2) {
+            // one-hot over features 18..29 as bf16 pairs: pair k holds features 18+2k, 19+2k; chunk 2 = [hdr, pair 0, 1, 2],
+            // chunk 3 = [pair 3, 4, 5, 0]
+            const int r = hot - 18 - (c == 2 ? -2 : 6);  // position of the hot feature relative to this chunk's word 0
+            v.x |= r == 0 ? 0x3F80u : r == 1 ? 0x3F800000u : 0u;
+            v.y = r == 2 ? 0x3F80u : r == 3 ? 0x3F800000u : 0u;
+            v.z = r == 4 ? 0x3F80u : r == 5 ? 0x3F800000u : 0u;
+            v.w = r == 6 ? 0x3F80u : r == 7 ? 0x3F800000u : 0u;
         }
+        base[chunk_u4(px, c)] = v;
     }
 }
 
@@ -183,6 +238,8 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
     // words (two independent coalesced loads); the winner's copies are then shuffled out of the lane
     // that scored it, so the next level starts from registers instead of re-reading nodes[cur] /
     // meta[cur] / meta[child].
+    const bool prof = P.dbg != nullptr;
+    const long long pc0 = prof ? clock64() : 0;
     Node tn = nodes[cur];
     u32 m = meta[cur];
     for (;;) {
@@ -269,6 +326,7 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
     }
     if (depth > 0) pos.check = in_check(pos);
     __syncwarp();
+    const long long pc1 = prof ? clock64() : 0;
     if (lane == 0 && scanned) atomicAdd(&P.stats->children_scanned, scanned);
     // A node is one move sequence from the game start, so its terminal status never changes: the
     // first visit caches it in the (otherwise unused) child0 word of the childless node and the
@@ -298,6 +356,10 @@ __device__ bool select_once(const PoolDev& P, int t, WarpScratch& s) {
         c.leaf_nact = n;
         c.depth = depth;
         c.state = 1;
+        if (prof) {  // slots 3 / 4 of the select profile: descent and leaf (terminal test + legal actions) cycles
+            P.dbg[(size_t)t * 8 + 3] = pc1 - pc0;
+            P.dbg[(size_t)t * 8 + 4] = clock64() - pc1;
+        }
     }
     __syncwarp();
     return true;
@@ -776,7 +838,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P,
     if (prof && lane_id() == 0) {
         t_enc = clock64() - c0;
         long long* d = P.dbg + (size_t)t * 8;
-        d[0] = clock64() - t0; d[1] = t_sel; d[2] = n_sel; d[3] = t_move; d[4] = n_move; d[5] = t_enc; d[6] = c.depth; d[7] = c.leaf_nact;
+        d[0] = clock64() - t0; d[1] = t_sel; d[2] = n_sel; if (n_move) { d[3] = -t_move; d[4] = -n_move; } d[5] = t_enc; d[6] = c.depth; d[7] = c.leaf_nact;
     }
 }
 
@@ -800,7 +862,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P,
 __global__ void k_tree_select(PoolDev P, int t, float* obs, int* need_eval) {
     __shared__ WarpScratch s;
     const bool r = select_once(P, t, s);
-    if (r) warp_encode_f32(P.ctl[t].leaf_pos, obs);
+    if (r) warp_encode_f32(P.ctl[t].leaf_pos, obs, s.fbuf, reinterpret_cast<signed char*>(s.sorted_ok));
     if (lane_id() == 0) *need_eval = r ? 1 : 0;
 }
 __global__ void k_tree_expand(PoolDev P, int t, const float* policy, float value, int disable_bootstrap) {
@@ -891,10 +953,13 @@ __global__ void k_tree_digest(PoolDev P, int t, u64* out) {
 
 // Batched position kernels -------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_encode_f32(const Pos* pos, int n, float* obs) {
-    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    __shared__ float hdr[4][20];
+    __shared__ signed char hot[4][64];
+    const int w = threadIdx.x >> 5;
+    const int b = blockIdx.x * 4 + w;
     if (b >= n) return;
     const Pos p = pos[b];
-    warp_encode_f32(p, obs + (size_t)b * 64 * NFEATURES);
+    warp_encode_f32(p, obs + (size_t)b * 64 * NFEATURES, hdr[w], hot[w]);
 }
 __global__ void __launch_bounds__(128) k_encode_tall(const Pos* pos, int n, uint4* planes) {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -1019,7 +1084,7 @@ __global__ void k_env_query(EnvDev e, int ops, int arg, float farg, EnvQuery* q,
         if ((ops & 1) && nact >= 0)
             for (int i = lane; i < nact; i += 32) actions[i] = outbuf[i];
     }
-    if (ops & 4) warp_encode_f32(p, obs);
+    if (ops & 4) warp_encode_f32(p, obs, s.fbuf, reinterpret_cast<signed char*>(s.sorted_ok));
     if (lane == 0) {
         if (ops & 8) q->bootstrap = bootstrap_value(p, farg);
         if (ops & 16) q->code = encode_action(p, (u16)arg);

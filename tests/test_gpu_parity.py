@@ -92,6 +92,44 @@ def test_batched_positions_vs_oracle_large(kb):
         assert np.array_equal(nxt[i:i + 1].view(np.uint8).reshape(-1), e.export()), i
 
 
+def _tall_from_obs(obs):
+    """numpy restatement of csrc/layout.cuh: fp32 [n][64][30] planes -> bf16 tall image [items][640][64] (as uint16):
+    board slot s, square q sits at pixel (1 + 9 s + q // 8) * 10 + 1 + q % 8; the 16-byte chunk with channels 8j..8j+7
+    of pixel px is stored at chunk slot j ^ (px & 7); everything else is zero."""
+    n = len(obs)
+    items = (n + 6) // 7
+    tall = np.zeros((items, 640, 64), np.uint16)
+    bf = (np.ascontiguousarray(obs, np.float32).reshape(n, 64, 30).view(np.uint32) >> 16).astype(np.uint16)  # exact in bf16
+    for b in range(n):
+        item, slot = divmod(b, 7)
+        for q in range(64):
+            px = (1 + 9 * slot + q // 8) * 10 + 1 + q % 8
+            line = np.zeros(64, np.uint16)
+            line[:30] = bf[b, q]
+            for j in range(8):
+                k = j ^ (px & 7)
+                tall[item, px, 8 * k:8 * k + 8] = line[8 * j:8 * j + 8]
+    return tall
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 50, 0])
+def test_tall_bf16_encoder_bit_exact(kb, n):
+    """north_star kernel 1 in the tower's own input layout: every byte of the bf16 tall image equals the REFERENCE's
+    planes (golden fixture generated from the compiled reference's Env::observe) rearranged by the layout rule; pads and
+    unused channels stay zero (ragged last item too).  n = 0 takes every golden position."""
+    from kami_b200 import api
+
+    z = np.load(os.path.join(G, "positions.npz"))
+    pos = api.as_positions(z["pos"])
+    planes = z["planes"].astype(np.float32).reshape(len(pos), -1)
+    if n:
+        idx = np.linspace(0, len(pos) - 1, n).astype(int)
+        pos, planes = pos[idx], planes[idx]
+    got, tail = api.encode_planes_tall(pos)
+    assert np.array_equal(got, _tall_from_obs(planes))
+    assert not tail.any()
+
+
 def test_empty_batches(kb):
     from kami_b200 import api
 
