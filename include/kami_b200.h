@@ -185,6 +185,12 @@ int kb_pool_set_policy_mode(kb_pool* p, int dense);
 /* replay sink: finished-game samples (selfplay.cpp:141-188) kept on the device as sparse rows */
 int kb_pool_drain_samples(kb_pool* p, int max_samples, float* obs /*[m][1920]*/, float* pi /*[m][4672]*/, float* z /*[m]*/, int* count);
 
+/* Selfplay::get_next_pgn (selfplay.h:73-80, selfplay.cpp:167-171): request the action list of the next self-play game
+ * that finishes inside kb_pool_step, then poll for it (count = 0 until one has finished).  Replaying the actions on a
+ * kami::Env gives Env::pgn(). */
+int kb_pool_request_game(kb_pool* p);
+int kb_pool_take_game(kb_pool* p, int32_t* actions, int cap, int* count);
+
 /* timing helper: elapsed ms of the last kb_pool_step / kb_net_forward_dev per phase */
 typedef struct kb_phase_ms {
     float select, encode, tower, heads, expand, total;

@@ -192,21 +192,82 @@ class Env {
         fen += " " + std::to_string((int)p.hmc) + " " + std::to_string(1 + (int)history.size() / 2);
         return fen;
     }
-    // Movetext of the finished game.  The reference prints SAN through the vendored thc library
-    // (env.h:432-474); this build writes long-algebraic (UCI) moves instead -- out of scope, see
-    // DESIGN.md section 7.
+    // Movetext of the finished game in SAN (reference: env.h:432-474, which prints through the vendored thc library's
+    // Move::NaturalOut, thc.cpp:6974-7188).  Same conventions: "e4" / "exf6" (en passant too) / "=N" suffixes, "O-O",
+    // piece moves disambiguated by file, then rank, then both, and only against LEGAL moves of the same piece letter to
+    // the same square; "+" for check, "#" for mate.  The game is replayed on a scratch device env; the rules are this
+    // library's (= neocortex's), so a queen "promotion" that the reference's own rules never carry out (the
+    // pawn stays a pawn) is written as the plain pawn move it is -- thc would print "=Q" there and lose track of the game.
     std::string pgn() {
         float value;
         std::string tstr;
         if (!terminal_str(&value, tstr)) throw std::runtime_error("Game must be in terminal state to write PGN!");
+        struct Scratch {
+            kb_env* e = nullptr;
+            Scratch() { kb_check(kb_env_create(&e)); }
+            ~Scratch() { kb_env_destroy(e); }
+        } sc;
+        auto type_at = [](const kb_position& p, int sq) {
+            for (int i = 0; i < 6; ++i)
+                if (p.pieces[i] >> sq & 1) return i;
+            return -1;
+        };
+        auto legal_moves = [&](std::vector<ncMove>& out) {
+            int32_t buf[KB_MAX_ACTIONS];
+            int n = 0;
+            kb_check(kb_env_actions(sc.e, buf, KB_MAX_ACTIONS, &n));
+            out.resize(n);
+            for (int i = 0; i < n; ++i) kb_check(kb_env_decode(sc.e, buf[i], &out[i]));
+        };
         std::string out;
         int mn = 1;
+        kb_position pos;
+        std::vector<ncMove> legal, next_legal;
+        kb_check(kb_env_position(sc.e, &pos));
+        legal_moves(legal);
         for (size_t i = 0; i < history.size(); ++i) {
             if (i % 2 == 0) out += (mn == 1 ? "" : " ") + std::to_string(mn) + ".";
             else ++mn;
-            char uci[6];
-            ncMoveUCI(history[i], uci);
-            out += std::string(" ") + uci;
+            const ncMove mv = history[i];
+            const int src = ncMoveSrc(mv), dst = ncMoveDst(mv), promo = ncMovePtype(mv);
+            const int piece = type_at(pos, src);
+            const bool capture = type_at(pos, dst) >= 0 || (piece == 0 && pos.ep != 0xFF && dst == pos.ep);
+            const char sf = (char)('a' + src % 8), sr = (char)('1' + src / 8), df = (char)('a' + dst % 8), dr = (char)('1' + dst / 8);
+            std::string san;
+            if (piece == 0) {
+                if (capture) san = std::string(1, sf) + "x";
+                san += df;
+                san += dr;
+                if (promo >= 1 && promo <= 4) san += std::string("=") + "PNBRQ"[promo];
+            } else if (piece == 5 && (dst % 8 - src % 8 == 2 || dst % 8 - src % 8 == -2)) {
+                san = dst % 8 > src % 8 ? "O-O" : "O-O-O";
+            } else {
+                // thc tries "Nd2", "Nbd2", "N1d2", "Nb1d2" in turn and keeps the first that exactly one legal move prints as
+                int same = 0, same_file = 0, same_rank = 0;
+                for (ncMove o : legal)
+                    if (ncMoveDst(o) == dst && type_at(pos, ncMoveSrc(o)) == piece) {
+                        ++same;
+                        same_file += ncMoveSrc(o) % 8 == src % 8;
+                        same_rank += ncMoveSrc(o) / 8 == src / 8;
+                    }
+                san = std::string(1, "PNBRQK"[piece]);
+                if (same != 1) {
+                    if (same_file == 1) san += sf;
+                    else if (same_rank == 1) san += sr;
+                    else san += sf, san += sr;
+                }
+                if (capture) san += 'x';
+                san += df;
+                san += dr;
+            }
+            int a = 0;
+            kb_check(kb_env_encode(sc.e, mv, &a));
+            kb_check(kb_env_push(sc.e, a));
+            kb_check(kb_env_position(sc.e, &pos));
+            legal_moves(next_legal);
+            if (pos.check) san += next_legal.empty() ? '#' : '+';
+            legal.swap(next_legal);
+            out += " " + san;
         }
         std::string result = value < 0 ? "0-1" : value > 0 ? "1-0" : "1/2-1/2";
         return out + " " + result + " {" + tstr + "}";

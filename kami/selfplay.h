@@ -67,7 +67,13 @@ class Selfplay {
     };
     Status status;
     ReplayBuffer& get_rbuf() { return replay_buffer; }
-    std::string get_next_pgn() { throw std::runtime_error("PGN export is not built (thc SAN printing is out of scope)"); }
+    // selfplay.h:73-80: the next game an inference thread finishes is written out as PGN movetext
+    std::string get_next_pgn() {
+        wants_pgn = true;
+        while (wants_pgn && status.code() == RUNNING) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        std::lock_guard<std::mutex> lock(pgn_lock);
+        return ret_pgn;
+    }
 
    private:
     std::vector<std::thread> inference, training;
@@ -75,6 +81,8 @@ class Selfplay {
     ReplayBuffer replay_buffer;
     int ibatch, nodes;
     std::atomic<bool> wants_pgn;
+    std::string ret_pgn;
+    std::mutex pgn_lock;
     std::list<std::atomic<int>> partial_trajectories;
 
     void inference_main(int id) {
@@ -99,6 +107,8 @@ class Selfplay {
         kb_pool* pool = nullptr;
         kb_check(kb_pool_create(&pool, ibatch, options::getInt("b200_node_capacity", 1 << 18), &cfg));
         std::vector<float> obs((size_t)64 * OBSIZE), pi((size_t)64 * PSIZE), z(64);
+        std::vector<int32_t> game_actions(2048);
+        bool game_requested = false;
         auto partial = partial_trajectories.begin();
         std::advance(partial, id);
         while (status.code() == RUNNING) {
@@ -111,6 +121,29 @@ class Selfplay {
                 kb_check(kb_pool_drain_samples(pool, 64, obs.data(), pi.data(), z.data(), &m));
                 for (int i = 0; i < m; ++i) replay_buffer.add(&obs[(size_t)i * OBSIZE], &pi[(size_t)i * PSIZE], z[i]);
             } while (m == 64);
+            // selfplay.cpp:167-171: hand the next finished game to get_next_pgn().  The device keeps the moves of the
+            // game; its movetext is written by replaying them on an Env.
+            if (!game_requested && wants_pgn.load()) {
+                kb_check(kb_pool_request_game(pool));
+                game_requested = true;
+            }
+            if (game_requested) {
+                int n = 0;
+                kb_check(kb_pool_take_game(pool, game_actions.data(), (int)game_actions.size(), &n));
+                if (n > 0) {
+                    game_requested = false;
+                    if (wants_pgn.load()) {
+                        Env env;
+                        for (int i = 0; i < n; ++i) env.push(game_actions[i]);
+                        std::string text = env.pgn();
+                        {
+                            std::lock_guard<std::mutex> lock(pgn_lock);
+                            ret_pgn = text;
+                        }
+                        wants_pgn = false;
+                    }
+                }
+            }
         }
         kb_pool_destroy(pool);
         std::cout << "Terminating inference thread: " << id << std::endl;

@@ -148,6 +148,8 @@ _SIGS = {
     "kb_pool_reset_stats": (C.c_int, [_P]),
     "kb_pool_set_policy_mode": (C.c_int, [_P, C.c_int]),
     "kb_pool_set_hostio_groups": (C.c_int, [_P, C.c_int]),
+    "kb_pool_request_game": (C.c_int, [_P]),
+    "kb_pool_take_game": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     "kb_pool_drain_samples": (C.c_int, [_P, C.c_int, _f32p, _f32p, _f32p, _i32p]),
     "kb_pool_last_phase_ms": (C.c_int, [_P, C.POINTER(PhaseMs)]),
     "kb_pool_debug_select_profile": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int]),
@@ -516,6 +518,17 @@ class TreePool:
     def set_policy_mode(self, dense):
         """0: softmax over the legal moves only (default); 1: dense softmax over all 4672 actions."""
         _ck(self.L.kb_pool_set_policy_mode(self.h, int(dense)))
+
+    def request_game(self):
+        """Selfplay::get_next_pgn: ask for the moves of the next game that finishes."""
+        _ck(self.L.kb_pool_request_game(self.h))
+
+    def take_game(self, cap=2048):
+        """Action list of the requested finished game, or None while no game has finished."""
+        buf = np.zeros(cap, np.int32)
+        n = C.c_int()
+        _ck(self.L.kb_pool_take_game(self.h, _vp(buf), cap, C.byref(n)))
+        return buf[: n.value].copy() if n.value else None
 
     def set_hostio_groups(self, groups):
         """step_hostio pipelines: groups of trees with their own NN::infer batch and streams (0 = default)."""

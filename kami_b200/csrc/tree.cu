@@ -655,6 +655,7 @@ __device__ void play_move(const PoolDev& P, int t, WarpScratch& s) {
         return;
     }
     if (lane == 0) {
+        if (c.traj_len < P.traj_cap) P.traj[(size_t)t * P.traj_cap + c.traj_len].action = action;
         c.traj_len += 1;
         c.rng += 1;
         c.moves += 1;
@@ -693,6 +694,18 @@ __device__ void play_move(const PoolDev& P, int t, WarpScratch& s) {
                 const TrajSample* src = P.traj + (size_t)t * P.traj_cap + i;
                 ReplaySample* dst = P.replay + (slot0 + i) % (unsigned long long)P.replay_cap;
                 dst->z = value == 0.0f ? P.cfg.draw_value : __fmul_rn(src->pov, value);
+            }
+        }
+        // a host asked for the next finished game's moves: the first warp to finish one hands them over
+        int take = 0;
+        if (lane == 0 && *(volatile int*)P.game == 1) take = atomicCAS(P.game, 1, 2) == 1;
+        if (__shfl_sync(0xffffffffu, take, 0)) {
+            for (int i = lane; i < len; i += 32) P.game[2 + i] = P.traj[(size_t)t * P.traj_cap + i].action;
+            __syncwarp();
+            if (lane == 0) {
+                P.game[1] = len;
+                __threadfence();
+                atomicExch(P.game, 3);
             }
         }
         if (lane == 0) {
@@ -1240,9 +1253,12 @@ int kb_env_bootstrap(kb_env* e, float window, float* out) {
 }
 int kb_env_position(kb_env* e, kb_position* out) {
     KB_ARG(e && out, "env/out");
+    // on the library's stream: it is non-blocking, a legacy-stream copy would not wait for a pending reset / push
     int n = 0;
-    KB_CUDA(cudaMemcpy(&n, e->d.count, sizeof(int), cudaMemcpyDeviceToHost));
-    KB_CUDA(cudaMemcpy(out, e->d.stack + (n - 1), sizeof(Pos), cudaMemcpyDeviceToHost));
+    KB_CUDA(cudaMemcpyAsync(&n, e->d.count, sizeof(int), cudaMemcpyDeviceToHost, main_stream()));
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
+    KB_CUDA(cudaMemcpyAsync(out, e->d.stack + (n - 1), sizeof(Pos), cudaMemcpyDeviceToHost, main_stream()));
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
     return KB_OK;
 }
 
@@ -1477,6 +1493,8 @@ int kb_pool_create(kb_pool** out, int n_trees, int node_capacity, const kb_tree_
     KB_CUDA(cudaMalloc(&d.replay, (size_t)d.replay_cap * sizeof(ReplaySample)));
     KB_CUDA(cudaMalloc(&d.replay_head, sizeof(unsigned long long)));
     KB_CUDA(cudaMemsetAsync(d.replay_head, 0, sizeof(unsigned long long), main_stream()));
+    KB_CUDA(cudaMalloc(&d.game, sizeof(int) * (size_t)(2 + d.traj_cap)));
+    KB_CUDA(cudaMemsetAsync(d.game, 0, sizeof(int) * (size_t)(2 + d.traj_cap), main_stream()));
     KB_CUDA(cudaMalloc(&p->obs_dev, sizeof(float) * KB_OBSIZE));
     KB_CUDA(cudaMalloc(&p->pol_dev, sizeof(float) * KB_PSIZE));
     KB_CUDA(cudaMalloc(&p->int_dev, sizeof(int) * 4));
@@ -1502,7 +1520,7 @@ int kb_pool_destroy(kb_pool* p) {
     cudaStreamSynchronize(main_stream());
     PoolDev& d = p->d;
     cudaFree(d.nodes); cudaFree(d.meta); cudaFree(d.ctl); cudaFree(d.error); cudaFree(d.stats);
-    cudaFree(d.traj); cudaFree(d.replay); cudaFree(d.replay_head);
+    cudaFree(d.traj); cudaFree(d.replay); cudaFree(d.replay_head); cudaFree(d.game);
     cudaFree(p->obs_dev); cudaFree(p->pol_dev); cudaFree(p->int_dev); cudaFree(p->u64_dev); cudaFree(p->info_dev);
     cudaFree(p->child_i); cudaFree(p->child_f); cudaFree(p->leaf_dev); cudaFree(p->policy_dev); cudaFree(p->value_dev);
     cudaFree(p->obs_batch_dev); cudaFree(d.dbg);
@@ -1704,6 +1722,7 @@ int kb_pool_select(kb_pool* p) {
 }
 int kb_pool_leaf_positions(kb_pool* p, kb_position* out) {
     KB_ARG(p && out, "pool/out");
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
     KB_CUDA(cudaMemcpy(out, p->leaf_dev, sizeof(Pos) * (size_t)p->d.n_trees, cudaMemcpyDeviceToHost));
     return KB_OK;
 }
@@ -1965,6 +1984,31 @@ int kb_pool_last_phase_ms(kb_pool* p, kb_phase_ms* out) {
 
 // Expands the device-side sparse samples into the reference's replay rows
 // (obs[1920], mcts[4672], result) -- selfplay.cpp:176-186, replaybuffer.h:36-56.
+// Selfplay::get_next_pgn (selfplay.h:73-80): ask for the moves of the next game that finishes, then poll.
+int kb_pool_request_game(kb_pool* p) {
+    KB_ARG(p, "pool");
+    int one = 1;
+    KB_CUDA(cudaMemcpyAsync(p->d.game, &one, sizeof(int), cudaMemcpyHostToDevice, main_stream()));
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
+    return KB_OK;
+}
+int kb_pool_take_game(kb_pool* p, int32_t* actions, int cap, int* count) {
+    KB_ARG(p && actions && count && cap > 0, "pool/actions/cap/count");
+    *count = 0;
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
+    int hdr[2] = {0, 0};
+    KB_CUDA(cudaMemcpy(hdr, p->d.game, sizeof(hdr), cudaMemcpyDeviceToHost));
+    if (hdr[0] != 3) return KB_OK;  // nothing yet (or nothing requested)
+    if (hdr[1] > cap) {
+        set_error("game of %d moves does not fit the caller's buffer of %d", hdr[1], cap);
+        return KB_ERR_CAPACITY;
+    }
+    KB_CUDA(cudaMemcpy(actions, p->d.game + 2, sizeof(int) * (size_t)hdr[1], cudaMemcpyDeviceToHost));
+    KB_CUDA(cudaMemset(p->d.game, 0, sizeof(int)));
+    *count = hdr[1];
+    return KB_OK;
+}
+
 int kb_pool_drain_samples(kb_pool* p, int max_samples, float* obs, float* pi, float* z, int* count) {
     KB_ARG(p && count, "pool/count");
     KB_CUDA(cudaStreamSynchronize(main_stream()));

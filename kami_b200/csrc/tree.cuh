@@ -49,7 +49,7 @@ struct TrajSample {
     float pov;
     int root_n;
     int nchild;
-    int pad;
+    int action;  // the move played from this position (selfplay.cpp:157-161)
     u32 entry[TRAJ_MAX_CHILD];  // action << 16 | visits
 };
 struct ReplaySample {
@@ -97,6 +97,8 @@ struct PoolDev {
     ReplaySample* replay;
     int replay_cap;
     unsigned long long* replay_head;
+    int* game;  // [0] state: 0 idle, 1 requested, 2 being written, 3 ready; [1] length; [2..] actions of one finished
+                // game (Selfplay::get_next_pgn, selfplay.h:73-80 / selfplay.cpp:167-171)
     Cfg cfg;
     long long* dbg;     // optional [n_trees][8] cycle counters of the last k_pool_select (kb_pool_debug_select_profile)
     int defer_compact;  // batched loops: push only flags a full arena, k_pool_compact (a block per tree) copies

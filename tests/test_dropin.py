@@ -103,3 +103,54 @@ def test_selfplay_train_arena_loop_smoke(kb):
     assert "TRAIN 0: training generation 0 with 48 trajectories" in text, text[-800:]
     assert "EVAL 0: evaluating model generation 1" in text
     assert ("candidate accepted" in text) or ("candidate rejected" in text)
+
+
+@pytest.mark.gpu
+def test_env_pgn_matches_reference_movetext(kb):
+    """Env::pgn() (kami/env.h, SAN written on this library's rules) against the movetext the UNMODIFIED reference prints
+    through the vendored thc library (tests/golden/pgn_games.json, made by tests/golden/make_pgn_golden.py): 16 seeded
+    games, 2 716 plies with mates, checks, en-passant and ordinary captures, under-promotions, castling and file / rank
+    disambiguation.  Games with a queen "promotion" are not in the fixture: the reference's own output is undefined
+    there (the thc board promotes, the reference's game does not)."""
+    import json
+
+    exe = os.path.join(DROPIN, "pgn_check")
+    if not os.path.exists(exe):
+        pytest.skip("kami/_dropin not built")
+    games = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pgn_games.json")))
+    text = "".join("%d %s\n" % (len(g["actions"]), " ".join(map(str, g["actions"]))) for g in games)
+    out = subprocess.run([exe], input=text.encode(), capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-400:]
+    got = [ln[4:] for ln in out.stdout.decode().splitlines() if ln.startswith("PGN ")]
+    assert len(got) == len(games)
+    for g, mine in zip(games, got):
+        assert mine == g["pgn"], (mine[-120:], g["pgn"][-120:])
+
+
+@pytest.mark.gpu
+def test_pool_hands_over_a_finished_game(kb):
+    """Selfplay::get_next_pgn's device half (kb_pool_request_game / kb_pool_take_game): the action list of the next
+    game that finishes replays legally on an Env to a terminal position."""
+    import numpy as np
+    import harness as H
+    import nn_oracle as NO
+    from kami_b200 import api
+
+    net = kb.NN(64, 1)
+    net.load_blob(NO.pack_blob(NO.init_params(64, 1, seed=3), 64, 1))
+    pool = kb.TreePool(64, 1 << 14, api.tree_cfg(noise_weight=0.05, selfplay_nodes=4, seed=5, alpha_initial=1.0, alpha_final=1.0, **H.DEF_YML))
+    assert pool.take_game() is None  # nothing requested
+    pool.request_game()
+    game = None
+    for _ in range(400):
+        pool.step(net, 16)
+        game = pool.take_game()
+        if game is not None:
+            break
+    assert game is not None and len(game) > 4
+    env = kb.Env()
+    for a in game:
+        assert int(a) in [int(x) for x in env.actions()]
+        env.push(int(a))
+    assert env.terminal()[0]
+    assert pool.take_game() is None  # handed over once
