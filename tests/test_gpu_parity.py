@@ -444,6 +444,38 @@ def test_pool_step_selfplay_smoke(kb):
             assert abs(float(p.sum()) - 1.0) < 1e-3
 
 
+def test_pool_full_size_config3_properties(kb):
+    """BASELINE config 3 at full size: 1024 concurrent games, options.def.yml (2x64 tower, 1024-node budget per move),
+    through properties that do not need the oracle: exactly one evaluation per tree per step, every tree moves when its
+    root reaches the budget, per-tree visit accounting (n(root) = 1 + sum of child visits), priors that sum to 1, finished
+    games only with z in {-1, draw_value, +1} -- and the whole run is deterministic: a second pool with the same seeds
+    reaches bit-identical trees (same digests), noise on, which would expose any race between trees or kernels."""
+    F, R, n, nodes = 64, 2, 1024, 1024
+    net = kb.NN(F, R)
+    net.load_blob(NO.pack_blob(NO.init_params(F, R, seed=1), F, R))
+    kw = dict(noise_weight=0.05, selfplay_nodes=nodes, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5, alpha_cutoff=20,
+              draw_value_pct=50, seed=77, **H.DEF_YML)
+    iters = 2 * nodes + 100  # every tree plays at least two moves
+    digests = []
+    for rep in range(2):
+        pool = kb.TreePool(n, 1 << 17, _cfg(kb, **kw))
+        pool.step(net, iters)
+        s = pool.stats()
+        assert s["evals"] == n * iters
+        assert s["moves"] >= 2 * n and s["path_nodes"] >= s["evals"] and s["children_created"] > 10 * s["evals"]
+        for i in (0, 1, 333, 512, n - 1):
+            t = pool.tree(i)
+            a, cn, w, p = t.root_children()
+            assert len(cn) > 0 and t.n() == 1 + int(cn.sum()) and t.n() < nodes
+            assert abs(float(p.sum()) - 1.0) < 1e-3
+        digests.append([pool.tree(i).digest() for i in range(0, n, 37)])
+        obs, pi, z = pool.drain_samples(256)
+        if len(z):
+            assert np.allclose(pi.sum(1), 1.0, atol=1e-3) and set(np.unique(z)).issubset({-1.0, 0.0, 1.0})
+        del pool
+    assert digests[0] == digests[1]
+
+
 @pytest.mark.parametrize("F,R,groups,vmode", [(64, 1, 1, 0), (64, 1, 4, 1), (64, 1, 3, 1), (128, 1, 4, 1)])
 def test_pool_step_matches_hostio_path(kb, F, R, groups, vmode):
     """kb_pool_step (resident) and kb_pool_step_hostio (reference-shaped host round trip) drive
