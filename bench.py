@@ -545,6 +545,24 @@ def run_ours(args, rank, world, local, dist):
         except Exception as e:
             if rank == 0:
                 extras["train_20x256"] = {"error": str(e)}
+    if not args.no_extras and world > 1 and 8192 % world == 0:
+        # BASELINE config 4 exactly: 8192 concurrent games in total, sharded by game over the N GPUs (8192 / N trees per
+        # GPU, no collective), same network and budget.  The headline line above keeps 1024 trees per GPU (weak scaling).
+        try:
+            per = 8192 // world
+            pool4 = kami_b200.TreePool(per, NODE_CAPACITY, api.tree_cfg(seed=per_rank_seed(5000, rank), **kw))
+            pool4.step(net, args.preroll if args.preroll > 0 else 64)
+            pool4.reset_stats()
+            k4 = max(3, min(args.steps, 400))
+            ms4 = timed_steps(lambda k: pool4.step(net, k), k4)
+            ev4 = reduce_sum(dist, local, float(pool4.stats()["evals"]))
+            if rank == 0:
+                extras["config4_8192_games"] = {"trees_per_gpu": per, "n_gpus": world, "steps": k4, "ms_per_step": ms4 / k4,
+                                                "evals_per_sec": ev4 / (ms4 * 1e-3), "scaling": "strong (8192 games in total)"}
+            del pool4
+        except Exception as e:
+            if rank == 0:
+                extras["config4_8192_games"] = {"error": str(e)}
     for p in bufs:
         L.kb_host_free_pinned(p)
     if rank != 0:
