@@ -69,20 +69,21 @@ __device__ __forceinline__ void block_channel_sums(float (&a)[8], float (&q)[8],
     }
 }
 
+constexpr int BN_U = 4;  // pixel lines in flight per thread and trip (8 measured the same and spills)
 // ---- BatchNorm forward (training mode) ---------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bn_stats(const uint4* pre, int boards, int slabs, float* sum, float* sumsq) {
+__global__ void __launch_bounds__(256, 2) k_bn_stats(const uint4* pre, int boards, int slabs, float* sum, float* sumsq) {
     const int s = blockIdx.x, j = threadIdx.x & 7, pl = threadIdx.x >> 3;
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int npix = boards * 64, stride = gridDim.y * 32;
-    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {  // four independent loads in flight per thread
-        uint4 v[4];
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += BN_U * stride) {  // BN_U independent loads in flight per thread
+        uint4 v[BN_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             const int g = g0 + u * stride;
             v[u] = g < npix ? pre[act_idx(g >> 6, g & 63, slabs, s, j)] : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             float f[8];
             unpack8(v[u], f);
 #pragma unroll
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) k_bn_stats(const uint4* pre, int boards, 
 // sum / sumsq: this layer's own accumulators (zeroed once per step).  Every thread derives mean / rstd of its 8
 // channels; blocks with blockIdx.y == 0 publish them for the backward pass and update the running statistics
 // (momentum 0.1, unbiased variance: LibTorch BatchNorm2d defaults).
-__global__ void __launch_bounds__(256) k_bn_apply(const uint4* pre, uint4* post, const uint4* skip, int boards, int slabs, const float* sum,
+__global__ void __launch_bounds__(256, 2) k_bn_apply(const uint4* pre, uint4* post, const uint4* skip, int boards, int slabs, const float* sum,
                                                   const float* sumsq, float n, float* mean, float* rstd, float* run_mean, float* run_var,
                                                   const float* gamma, const float* beta) {
     const int s = blockIdx.x, j = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -119,18 +120,18 @@ __global__ void __launch_bounds__(256) k_bn_apply(const uint4* pre, uint4* post,
         }
     }
     const int npix = boards * 64, stride = gridDim.y * 32;
-    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
-        size_t idx[4];
-        uint4 v[4], sk[4];
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += BN_U * stride) {
+        size_t idx[BN_U];
+        uint4 v[BN_U], sk[BN_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             const int g = g0 + u * stride;
             idx[u] = g < npix ? act_idx(g >> 6, g & 63, slabs, s, j) : 0;
             v[u] = pre[idx[u]];
             sk[u] = skip ? skip[idx[u]] : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             if (g0 + u * stride >= npix) break;
             float f[8], t[8];
             unpack8(v[u], f);
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) k_bn_apply(const uint4* pre, uint4* post,
 
 // ---- BatchNorm + ReLU backward -----------------------------------------------------------------
 // dy: gradient w.r.t. the ReLU output.  s1 = sum(dy * mask), s2 = sum(dy * mask * xhat), mask = (gamma*xhat+beta > 0)
-__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const uint4* dy, const uint4* pre, int boards, int slabs, const float* mean, const float* rstd,
+__global__ void __launch_bounds__(256, 2) k_bn_bwd_reduce(const uint4* dy, const uint4* pre, int boards, int slabs, const float* mean, const float* rstd,
                                                        const float* gamma, const float* beta, float* s1, float* s2) {
     const int s = blockIdx.x, j = threadIdx.x & 7, pl = threadIdx.x >> 3;
     const int c0 = s * 64 + j * 8;
@@ -158,17 +159,17 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const uint4* dy, const ui
     }
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int npix = boards * 64, stride = gridDim.y * 32;
-    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
-        uint4 vx[4], vd[4];
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += BN_U * stride) {
+        uint4 vx[BN_U], vd[BN_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             const int g = g0 + u * stride;
             const size_t i = g < npix ? act_idx(g >> 6, g & 63, slabs, s, j) : 0;
             vx[u] = pre[i];
             vd[u] = g < npix ? dy[i] : make_uint4(0, 0, 0, 0);  // a zero gradient adds nothing to either sum
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             float x[8], d[8];
             unpack8(vx[u], x);
             unpack8(vd[u], d);
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const uint4* dy, const ui
     block_channel_sums(a, q, s1, s2, s * 64);
 }
 // dpre = gamma * rstd * (dy*mask - s1/n - xhat * s2/n)
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const uint4* dy, const uint4* pre, uint4* dpre, int boards, int slabs, const float* mean,
+__global__ void __launch_bounds__(256, 2) k_bn_bwd_apply(const uint4* dy, const uint4* pre, uint4* dpre, int boards, int slabs, const float* mean,
                                                       const float* rstd, const float* gamma, const float* beta, const float* s1, const float* s2, float n,
                                                       float* dgamma, float* dbeta) {
     const int s = blockIdx.x, j = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -204,18 +205,18 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const uint4* dy, const uin
         }
     }
     const int npix = boards * 64, stride = gridDim.y * 32;
-    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += 4 * stride) {
-        size_t idx[4];
-        uint4 vx[4], vd[4];
+    for (int g0 = blockIdx.y * 32 + pl; g0 < npix; g0 += BN_U * stride) {
+        size_t idx[BN_U];
+        uint4 vx[BN_U], vd[BN_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             const int g = g0 + u * stride;
             idx[u] = g < npix ? act_idx(g >> 6, g & 63, slabs, s, j) : 0;
             vx[u] = pre[idx[u]];
             vd[u] = dy[idx[u]];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BN_U; ++u) {
             if (g0 + u * stride >= npix) break;
             float x[8], d[8], o[8];
             unpack8(vx[u], x);
@@ -871,9 +872,19 @@ int t_repack(kb_trainer* t, cudaStream_t st) {
     return KB_OK;
 }
 
+// Two resident blocks per SM in total, each thread streaming BN_U pixel lines per trip: measured on the 20x256 step,
+// 592 x slabs one-trip blocks 13.3 ms, 74 x 4 blocks 12.3 ms (prologue parameter loads and block turnover dominate short
+// blocks); fewer than two blocks per SM loses again.
 dim3 bn_grid(int slabs, int boards) {
-    int y = (boards * 64 + 127) / 128;  // four pixels per thread and trip
-    if (y > 592) y = 592;
+    int y = (boards * 64 + 32 * BN_U - 1) / (32 * BN_U);
+    static int cap_blocks = 0;
+    if (!cap_blocks) {
+        const char* e = getenv("KB_BN_BLOCKS");
+        cap_blocks = e ? atoi(e) : 2 * sm_count();
+        if (cap_blocks < 1) cap_blocks = 2 * sm_count();
+    }
+    const int cap = cap_blocks / (slabs > 0 ? slabs : 1) > 0 ? cap_blocks / (slabs > 0 ? slabs : 1) : 1;
+    if (y > cap) y = cap;
     return dim3(slabs, y > 0 ? y : 1);
 }
 
