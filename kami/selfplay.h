@@ -107,7 +107,7 @@ class Selfplay {
         kb_pool* pool = nullptr;
         kb_check(kb_pool_create(&pool, ibatch, options::getInt("b200_node_capacity", 1 << 18), &cfg));
         std::vector<float> obs((size_t)64 * OBSIZE), pi((size_t)64 * PSIZE), z(64);
-        std::vector<int32_t> game_actions(2048);
+        std::vector<int32_t> game_actions(4096);
         bool game_requested = false;
         auto partial = partial_trajectories.begin();
         std::advance(partial, id);

@@ -523,7 +523,7 @@ class TreePool:
         """Selfplay::get_next_pgn: ask for the moves of the next game that finishes."""
         _ck(self.L.kb_pool_request_game(self.h))
 
-    def take_game(self, cap=2048):
+    def take_game(self, cap=4096):
         """Action list of the requested finished game, or None while no game has finished."""
         buf = np.zeros(cap, np.int32)
         n = C.c_int()

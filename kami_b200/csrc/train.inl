@@ -234,9 +234,18 @@ __global__ void __launch_bounds__(256, 2) k_bn_bwd_apply(const uint4* dy, const 
 // ---- weight packing (fp32 master -> bf16 operand blocks of k_conv / k_conv2) -------------------------
 // Logical conv: out channel o, in channel ci, tap t.  transpose_flip = 0: w[o][ci][t] (forward);
 // 1: w[ci][o][taps-1-t] (the dgrad conv: in/out swapped, kernel rotated by 180 degrees).
-__global__ void k_pack_conv(const float* w, int O, int I, int taps, int transpose_flip, uint16_t* dst, int n_tile, int kslices, int npass) {
-    const size_t total = (size_t)npass * kslices * taps * n_tile * 64;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+struct PackJob {
+    const float* w;
+    uint16_t* dst;
+    int O, I, taps, transpose_flip, n_tile, kslices, npass;
+    int block0, nblocks;  // this job's share of the fused launch
+};
+__device__ __forceinline__ void pack_conv_elems(const PackJob& J, size_t first, size_t step) {
+    const int O = J.O, I = J.I, taps = J.taps, transpose_flip = J.transpose_flip, n_tile = J.n_tile, kslices = J.kslices;
+    const float* __restrict__ w = J.w;
+    uint16_t* __restrict__ dst = J.dst;
+    const size_t total = (size_t)J.npass * kslices * taps * n_tile * 64;
+    for (size_t e = first; e < total; e += step) {
         const int within = (int)(e % ((size_t)n_tile * 64));
         const size_t blk = e / ((size_t)n_tile * 64);
         const int tap = (int)(blk % taps);
@@ -251,6 +260,14 @@ __global__ void k_pack_conv(const float* w, int O, int I, int taps, int transpos
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         dst[e] = *reinterpret_cast<const uint16_t*>(&h);
     }
+}
+// every conv of the network (forward blocks and, where needed, the transposed / rotated dgrad blocks) in ONE launch:
+// the 85 separate 6.6 us launches of the 20x256 net were launch-bound (0.56 ms per training step)
+__global__ void __launch_bounds__(256) k_pack_all(const PackJob* jobs, int njobs) {
+    int j = 0;
+    while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].block0) ++j;
+    const PackJob J = jobs[j];
+    pack_conv_elems(J, (size_t)((int)blockIdx.x - J.block0) * blockDim.x + threadIdx.x, (size_t)J.nblocks * blockDim.x);
 }
 
 // ---- wgrad: dW[co][ci][tap] += sum over pixels dy[p][co] * x[p + shift(tap)][ci] (tcgen05, MN-major operands) ------
@@ -816,6 +833,8 @@ struct kb_trainer {
     float *wpart = nullptr;   // k_wgrad_row partial sums: [subsets <= 49][9][<= 256][<= 256]
     size_t wpart_floats = 0;
     float last_loss = 0.0f;
+    void* pack_jobs = nullptr;  // device table of k_pack_all
+    int n_pack_jobs = 0, pack_blocks = 0;
 };
 
 namespace {
@@ -838,15 +857,6 @@ int t_alloc_act(kb_trainer* t, uint4** out, int slabs) {
     return r;
 }
 
-int t_pack(const float* w, const TConv& c, const Layer& L, bool transpose_flip, cudaStream_t st) {
-    const int npass = L.n_total / L.n_tile;
-    const size_t total = (size_t)npass * L.slabs_in * L.ntaps * L.n_tile * 64;
-    const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-    k_pack_conv<<<blocks, 256, 0, st>>>(w, c.O, c.I, c.k * c.k, transpose_flip ? 1 : 0, reinterpret_cast<uint16_t*>(L.w), L.n_tile, L.slabs_in, npass);
-    KB_CUDA(cudaGetLastError());
-    return KB_OK;
-}
-
 int t_layer(kb_trainer* t, Layer& L, int slabs_in, int ksteps, int n_total, int n_valid, int ntaps, const float* bias) {
     L.slabs_in = slabs_in;
     L.ksteps = ksteps;
@@ -864,11 +874,42 @@ int t_layer(kb_trainer* t, Layer& L, int slabs_in, int ksteps, int n_total, int 
 }
 
 int t_repack(kb_trainer* t, cudaStream_t st) {
-    for (auto& c : t->conv) {
-        int r = t_pack(t->params + c.w_off, c, c.fwd, false, st);
+    if (!t->pack_jobs) {  // the job table is fixed for the life of the trainer
+        std::vector<PackJob> jobs;
+        int block0 = 0;
+        auto add = [&](const TConv& c, const Layer& L, bool flip) {
+            PackJob J;
+            J.w = t->params + c.w_off;
+            J.dst = reinterpret_cast<uint16_t*>(L.w);
+            J.O = c.O;
+            J.I = c.I;
+            J.taps = c.k * c.k;
+            J.transpose_flip = flip ? 1 : 0;
+            J.n_tile = L.n_tile;
+            J.kslices = L.slabs_in;
+            J.npass = L.n_total / L.n_tile;
+            const size_t total = (size_t)J.npass * J.kslices * J.taps * J.n_tile * 64;
+            J.nblocks = (int)((total + 2047) / 2048 < 288 ? (total + 2047) / 2048 : 288);  // >= 8 elements per thread
+            if (J.nblocks < 1) J.nblocks = 1;
+            J.block0 = block0;
+            block0 += J.nblocks;
+            jobs.push_back(J);
+        };
+        for (auto& c : t->conv) {
+            add(c, c.fwd, false);
+            if (c.has_dgrad) add(c, c.dgrad, true);
+        }
+        void* d = nullptr;
+        int r = t_alloc(t, &d, sizeof(PackJob) * jobs.size(), false);
         if (r) return r;
-        if (c.has_dgrad && (r = t_pack(t->params + c.w_off, c, c.dgrad, true, st))) return r;
+        KB_CUDA(cudaMemcpyAsync(d, jobs.data(), sizeof(PackJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaStreamSynchronize(st));  // jobs is a local
+        t->pack_jobs = d;
+        t->n_pack_jobs = (int)jobs.size();
+        t->pack_blocks = block0;
     }
+    k_pack_all<<<t->pack_blocks, 256, 0, st>>>(reinterpret_cast<const PackJob*>(t->pack_jobs), t->n_pack_jobs);
+    KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
 

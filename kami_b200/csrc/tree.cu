@@ -31,6 +31,7 @@ int upload_tables() {
 // ------------------------------------------------------------------------------------------
 // warp helpers
 // ------------------------------------------------------------------------------------------
+constexpr int COMPACT_PERIOD = 8;  // batched loops run the block-cooperative collector every COMPACT_PERIOD selects
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -544,7 +545,12 @@ __device__ bool push_once(const PoolDev& P, int t, int action) {
     __syncwarp();
     // Re-rooting is free (the root index moves); the copying collector only runs when the arena
     // could not hold another move's worth of expansions.
-    const u32 reserve = P.cfg.selfplay_nodes > 0 && (u32)P.cfg.selfplay_nodes * 64u < P.cap / 2 ? (u32)P.cfg.selfplay_nodes * 64u : P.cap / 2;
+    // The reserve must also cover what the batched loops allocate between the flag and the deferred collector's next run:
+    // COMPACT_PERIOD selects with up to MAX_MOVES children each (tiny node budgets used to overflow here: 6 x 64 = 384
+    // nodes were less than eight expansions of ~50 children).
+    u32 reserve = P.cfg.selfplay_nodes > 0 ? (u32)P.cfg.selfplay_nodes * 64u : 0u;
+    if (reserve < (u32)(COMPACT_PERIOD + 2) * MAX_MOVES) reserve = (u32)(COMPACT_PERIOD + 2) * MAX_MOVES;
+    if (reserve > P.cap / 2) reserve = P.cap / 2;
     if (c.alloc + reserve > P.cap && !P.defer_compact) compact_into_other_space(P, t, keep);
     else if (lane == 0) {
         c.root = keep;
@@ -1478,7 +1484,10 @@ int kb_pool_create(kb_pool** out, int n_trees, int node_capacity, const kb_tree_
     d.tree_hi = n_trees;
     d.cap = (u32)node_capacity;
     d.cfg = to_dev_cfg(*cfg);
-    d.traj_cap = cfg->selfplay_nodes > 0 ? 640 : 1;
+    // plies recorded per running game (selfplay.cpp:150-151 keeps every position of the game).  Measured on 15 k near-random
+    // games (6-node budget): mean 290 plies, p99 466, max 579 -- the 50-ply rule (Q4) bounds a game by the irreversible moves
+    // it can contain.  2048 leaves a wide margin at 1.2 MB per tree; beyond it the pool reports KB_ERR_CAPACITY.
+    d.traj_cap = cfg->selfplay_nodes > 0 ? 2048 : 1;
     d.replay_cap = cfg->selfplay_nodes > 0 ? (n_trees * 64 < 16384 ? 16384 : n_trees * 64) : 1;
     const size_t nn = (size_t)n_trees * 2 * d.cap;
     KB_CUDA(cudaMalloc(&d.nodes, nn * sizeof(Node)));
@@ -1700,7 +1709,6 @@ static inline int pool_blocks(kb_pool* p) { return (p->d.n_trees + WARPS_PER_BLO
 
 // Select launch of the batched loops.  Arena compaction is deferred (push only flags a nearly full
 // arena; the reserve covers many more steps) and done by k_pool_compact every COMPACT_PERIOD selects.
-constexpr int COMPACT_PERIOD = 8;
 static int pool_launch_select(kb_pool* p, uint4* planes, Pos* leaf_out, cudaStream_t st) {
     PoolDev d = p->d;
     d.defer_compact = 1;
