@@ -444,6 +444,23 @@ def test_pool_step_selfplay_smoke(kb):
             assert abs(float(p.sum()) - 1.0) < 1e-3
 
 
+def test_pool_tiny_budget_long_run_keeps_arena_invariants(kb):
+    """Regression: at tiny node budgets a move is played every few steps and the arena reserve that triggers the deferred
+    collector (k_pool_compact, every 8th select) used to be smaller than what eight expansions allocate -> an
+    intermittent KB_ERR_CAPACITY.  Thousands of near-random games on small arenas must run through and keep the accounting
+    invariants."""
+    net = kb.NN(64, 1)
+    net.load_blob(NO.pack_blob(NO.init_params(64, 1, seed=2), 64, 1))
+    for nodes, cap in ((6, 1 << 14), (2, 1 << 12), (3, 1 << 13)):
+        n = 64
+        pool = kb.TreePool(n, cap, _cfg(kb, noise_weight=0.05, selfplay_nodes=nodes, seed=9, **H.DEF_YML))
+        iters = 12000
+        for _ in range(iters // 500):
+            pool.step(net, 500)
+        s = pool.stats()
+        assert s["evals"] == n * iters and s["games"] > 20 and s["samples"] <= s["moves"]
+
+
 def test_pool_full_size_config3_properties(kb):
     """BASELINE config 3 at full size: 1024 concurrent games, options.def.yml (2x64 tower, 1024-node budget per move),
     through properties that do not need the oracle: exactly one evaluation per tree per step, every tree moves when its
