@@ -408,6 +408,33 @@ def encoder_leg(api, L, pool, hbm_peak, peak_kind, n=131072, reps=10):
     return out
 
 
+def infer256_leg(api, L, pool, net, reps=20):
+    """BASELINE config 2 (the reference's test/nncuda.cpp / test/nn.cpp loop at batch 256): 256 synthetic positions ->
+    planes -> NN::infer through the host-buffer call (H2D observations, D2H policy [256][4672] + value inside the timed
+    region), next to the unmodified reference NN::infer (LibTorch CPU fp32, all host threads) on the same input."""
+    pos = pool.leaf_positions()[:256]
+    obs = api.encode_planes(pos)
+    out = {"batch": 256, "filters": FILTERS, "residuals": RESIDUALS}
+    net.infer(obs)
+    t0 = time.time()
+    for _ in range(reps):
+        pol, val = net.infer(obs)
+    dt = (time.time() - t0) / reps
+    out["ours"] = {"ms_per_call": dt * 1e3, "pred_per_sec": 256 / dt, "api": "kb_net_infer, pageable host buffers"}
+    import harness as H  # CPU baseline part only: the compiled reference under oracle/_ref
+
+    if H.ref_nn_lib() is not None:
+        nn = H.RefNN(FILTERS, RESIDUALS, seed=1, force_cpu=True)
+        H.ref_nn_lib().ref_nn_set_threads(max(1, os.cpu_count() or 1))
+        nn.infer(obs)
+        t0 = time.time()
+        for _ in range(3):
+            nn.infer(obs)
+        dr = (time.time() - t0) / 3
+        out["reference_cpu"] = {"ms_per_call": dr * 1e3, "pred_per_sec": 256 / dr, "cores": os.cpu_count() or 1}
+    return out
+
+
 def run_ours(args, rank, world, local, dist):
     numa = bind_to_gpu_numa(local)
     import kami_b200
@@ -529,6 +556,10 @@ def run_ours(args, rank, world, local, dist):
         except Exception as e:
             extras["roofline_encoder"] = {"error": str(e)}
         if world == 1:
+            try:
+                extras["config2_infer_256"] = infer256_leg(api, L, pool, net)
+            except Exception as e:
+                extras["config2_infer_256"] = {"error": str(e)}
             ev, mv, dt, kind = reference_loop(12.0, 3, 16)
             cores = os.cpu_count() or 1
             cpu = {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": kind, "positions_per_sec": mv / dt,
