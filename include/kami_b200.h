@@ -109,6 +109,8 @@ int kb_net_flops(kb_net* net, double* tower_flops, double* heads_flops); /* per 
 int kb_net_debug_activation(kb_net* net, int which, int board, float* out, int* channels);
 /* profiling hook: clock64 stamps of the fused tower kernel's phases (CTA 0) */
 int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, int* count);
+/* profiling hook: globaltimer (ns) at entry and exit of every CTA of the last fused tower launch, out[cta][2] */
+int kb_net_debug_cta_spans(kb_net* net, long long* out, int cap_ctas, int* count);
 
 /* ---- MCTS: kami/mcts.h:15-349; Selfplay::inference_main kami/selfplay.cpp:58-213 ---------- */
 typedef struct kb_tree_cfg {

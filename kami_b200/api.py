@@ -122,6 +122,7 @@ _SIGS = {
     "kb_trainer_debug_activation": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "kb_net_debug_activation": (C.c_int, [_P, C.c_int, C.c_int, _f32p, _i32p]),
     "kb_net_debug_timestamps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_longlong), C.c_int, _i32p]),
+    "kb_net_debug_cta_spans": (C.c_int, [_P, C.POINTER(C.c_longlong), C.c_int, _i32p]),
     "kb_tree_default_cfg": (C.c_int, [C.POINTER(TreeCfg)]),
     "kb_pool_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.POINTER(TreeCfg)]),
     "kb_pool_destroy": (C.c_int, [_P]),

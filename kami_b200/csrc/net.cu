@@ -806,6 +806,11 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
     const uint32_t ring_s = region_s + FZ_REGION;
 
     const int my_items = P.items > (int)blockIdx.x ? (P.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (P.ts && threadIdx.x == 0 && blockIdx.x < 160) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.ts[128 + 2 * blockIdx.x] = t;
+    }
     // PDL: this CTA may have become resident while the kernel before it on the stream (the pool's select) is still
     // draining.  Everything up to each role's pdl_wait() touches only this CTA's shared / tensor memory and constant
     // weights; planes, legal-action lists and the output rows are only touched after it.  Each role triggers the
@@ -1207,6 +1212,11 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+    if (P.ts && threadIdx.x == 0 && blockIdx.x < 160) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.ts[129 + 2 * blockIdx.x] = t;
+    }
 }
 
 // valueconv 1x1 (F -> 1) + BN + ReLU, Linear(64 -> 256), tanh (nn.cpp:83-88).  One block per
@@ -1909,8 +1919,8 @@ int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, in
     KB_REQUIRE_INIT();
     KB_ARG(net, "net");
     if (enable && !net->ts_dev) {
-        KB_CUDA(cudaMalloc(&net->ts_dev, 128 * sizeof(long long)));
-        KB_CUDA(cudaMemsetAsync(net->ts_dev, 0, 128 * sizeof(long long), main_stream()));
+        KB_CUDA(cudaMalloc(&net->ts_dev, (128 + 2 * 160) * sizeof(long long)));
+        KB_CUDA(cudaMemsetAsync(net->ts_dev, 0, (128 + 2 * 160) * sizeof(long long), main_stream()));
     }
     kb::g_conv_ts = enable && !net->fused ? net->ts_dev : nullptr;  // per-layer kernels: MMA-thread wait counters
     if (!out) kb::g_conv_ts_slot = 0;
@@ -1926,6 +1936,19 @@ int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, in
         cudaFree(net->ts_dev);
         net->ts_dev = nullptr;
     }
+    return KB_OK;
+}
+
+// profiling hook: globaltimer (ns) at entry and exit of every CTA of the last k_tower64 launch, [cta][2]
+int kb_net_debug_cta_spans(kb_net* net, long long* out, int cap_ctas, int* count) {
+    KB_REQUIRE_INIT();
+    KB_ARG(net && out && count && cap_ctas > 0, "net/out/count");
+    *count = 0;
+    if (!net->ts_dev) return KB_OK;
+    KB_CUDA(cudaStreamSynchronize(main_stream()));
+    const int n = cap_ctas < 160 ? cap_ctas : 160;
+    KB_CUDA(cudaMemcpy(out, net->ts_dev + 128, sizeof(long long) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+    *count = n;
     return KB_OK;
 }
 
