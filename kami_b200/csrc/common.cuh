@@ -31,7 +31,7 @@ bool initialized();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-int pdl_mask();  // KB_PDL_MASK: bit 0 select, bit 1 tower, bit 2 expand launched with the PDL attribute (A/B measurements)
+int pdl_mask();  // KB_PDL_MASK: bit 0 select, bit 1 tower, bit 2 expand, bit 3 fused expand+select launched with the PDL attribute
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

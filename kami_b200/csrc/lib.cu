@@ -24,7 +24,7 @@ int pdl_mask() {
     static int m = -1;
     if (m < 0) {
         const char* e = getenv("KB_PDL_MASK");
-        m = e ? atoi(e) & 7 : 3;  // select + tower; expand launched plainly (measured: PDL on expand costs 8-10 us per step)
+        m = e ? atoi(e) & 15 : 3;  // select + tower; expand launched plainly (measured: PDL on expand costs 8-10 us per step)
     }
     return m;
 }

@@ -824,14 +824,7 @@ __global__ void __launch_bounds__(256) k_pool_compact(PoolDev P) {
 
 // Batched select: the inner loop of selfplay.cpp:116-193 for every tree at once.
 // planes != nullptr: also writes the leaf's bf16 input planes (kernel 1 fused behind select).
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P, uint4* planes, Pos* leaf_out) {
-    __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
-    const int w = threadIdx.x >> 5;
-    const int t = P.tree0 + blockIdx.x * WARPS_PER_BLOCK + w;
-    pdl_launch_dependents();  // the tower's CTAs may move in (and set up) as this grid's blocks drain
-    pdl_wait();
-    if (t >= P.tree_hi) return;
-    WarpScratch& s = scratch[w];
+__device__ __forceinline__ void pool_select_tree(const PoolDev& P, int t, WarpScratch& s, uint4* planes, Pos* leaf_out) {
     TreeCtl& c = P.ctl[t];
     const bool prof = P.dbg != nullptr;
     long long t_move = 0, t_sel = 0, t_enc = 0, n_sel = 0, n_move = 0, c0 = 0, t0 = prof ? clock64() : 0;
@@ -860,8 +853,24 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P,
         d[0] = clock64() - t0; d[1] = t_sel; d[2] = n_sel; if (n_move) { d[3] = -t_move; d[4] = -n_move; } d[5] = t_enc; d[6] = c.depth; d[7] = c.leaf_nact;
     }
 }
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_select(PoolDev P, uint4* planes, Pos* leaf_out) {
+    __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
+    const int w = threadIdx.x >> 5;
+    const int t = P.tree0 + blockIdx.x * WARPS_PER_BLOCK + w;
+    pdl_launch_dependents();  // the tower's CTAs may move in (and set up) as this grid's blocks drain
+    pdl_wait();
+    if (t >= P.tree_hi) return;
+    pool_select_tree(P, t, scratch[w], planes, leaf_out);
+}
 
 // Batched expand + backup.  value_stride/value_mode implement NN::infer's value indexing (Q1).
+__device__ __forceinline__ void pool_expand_tree(const PoolDev& P, int t, WarpScratch& s, const float* policy, const float* value, int value_is_256,
+                                                 int disable_bootstrap, int compact) {
+    float v;
+    if (!value_is_256) v = value[t];
+    else v = P.cfg.value_index_mode == 0 ? value[t] /* vh.flat[t], nn.cpp:186 */ : value[(size_t)t * 256];
+    expand_once(P, t, policy + (size_t)t * (compact ? 128 : PSIZE), v, disable_bootstrap != 0, s, compact != 0);
+}
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P, const float* policy, const float* value, int value_is_256, int disable_bootstrap,
                                                                       int compact) {
     __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
@@ -871,10 +880,24 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand(PoolDev P,
     pdl_wait();
     if (t >= P.tree_hi) return;
     if (*P.error) return;
-    float v;
-    if (!value_is_256) v = value[t];
-    else v = P.cfg.value_index_mode == 0 ? value[t] /* vh.flat[t], nn.cpp:186 */ : value[(size_t)t * 256];
-    expand_once(P, t, policy + (size_t)t * (compact ? 128 : PSIZE), v, disable_bootstrap != 0, scratch[w], compact != 0);
+    pool_expand_tree(P, t, scratch[w], policy, value, value_is_256, disable_bootstrap, compact);
+}
+// expand of iteration i and select of iteration i + 1 in one launch (kb_pool_step): a tree's warp goes straight from its
+// backup to its next descent, so the slowest expand no longer holds back every select (and one launch boundary goes away).
+// Every value the trees read (Q1: tree t reads vh.flat[t], another board's output) was written by the tower before the
+// launch; a warp only writes its own tree, its own plane rows and its own leaf list.
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_pool_expand_select(PoolDev P, const float* policy, const float* value, int value_is_256,
+                                                                             int disable_bootstrap, int compact, uint4* planes, Pos* leaf_out) {
+    __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
+    const int w = threadIdx.x >> 5;
+    const int t = P.tree0 + blockIdx.x * WARPS_PER_BLOCK + w;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (t >= P.tree_hi) return;
+    if (*P.error) return;
+    pool_expand_tree(P, t, scratch[w], policy, value, value_is_256, disable_bootstrap, compact);
+    __syncwarp();
+    pool_select_tree(P, t, scratch[w], planes, leaf_out);
 }
 
 // Single-tree entry points (the kami::MCTS call protocol)
@@ -1769,22 +1792,40 @@ int kb_pool_step(kb_pool* p, kb_net* net, int iters) {
     // absorbs many terminal visits stretches its select)
     const int nsamp = iters < 32 ? iters : 32, stride = iters / nsamp;
     KB_CUDA(cudaEventRecord(p->ev[0], st));
+    auto is_timed = [&](int it) { return it % stride == 0 && it / stride < nsamp; };
+    static const bool fuse_ok = !(getenv("KB_NO_FUSED_EXPAND_SELECT") && atoi(getenv("KB_NO_FUSED_EXPAND_SELECT")));
+    bool have_leaf = false;  // this iteration's select already ran, fused behind the previous iteration's expand
     for (int it = 0; it < iters; ++it) {
         const int k = it / stride;
-        const bool timed = it % stride == 0 && k < nsamp;
-        if (timed) KB_CUDA(cudaEventRecord(p->evs[k][0], st));
-        if ((r = pool_launch_select(p, planes, nullptr, st))) return r;
-        if (timed) KB_CUDA(cudaEventRecord(p->evs[k][1], st));
+        const bool timed = is_timed(it);
+        if (!have_leaf) {
+            if (timed) KB_CUDA(cudaEventRecord(p->evs[k][0], st));
+            if ((r = pool_launch_select(p, planes, nullptr, st))) return r;
+            if (timed) KB_CUDA(cudaEventRecord(p->evs[k][1], st));
+            p->launches += 1;
+        }
         if (legal)  // softmax over the legal moves only: priors straight into p->policy_dev[tree][128]
             r = net_forward_legal_async(net, planes, n, &p->d.ctl[0].leaf_act[0], &p->d.ctl[0].leaf_nact, sizeof(TreeCtl), p->policy_dev, p->value_dev, st);
         else
             r = net_forward_async(net, planes, n, p->policy_dev, p->value_dev, st);
         if (r) return r;
         if (timed) KB_CUDA(cudaEventRecord(p->evs[k][2], st));
-        KB_CUDA(launch_pdl(2, k_pool_expand, dim3(pool_blocks(p)), dim3(32 * WARPS_PER_BLOCK), 0, st, p->d, (const float*)p->policy_dev,
-                           (const float*)p->value_dev, 1, 0, legal ? 1 : 0));
+        // expand(it) + select(it + 1) in one launch, unless a phase boundary is being timed, the deferred collector is due
+        // between the two (it needs every tree without a pending leaf) or this is the call's last iteration
+        const bool fuse = fuse_ok && it + 1 < iters && !timed && !is_timed(it + 1) && p->selects_since_compact % COMPACT_PERIOD != 0;
+        if (fuse) {
+            PoolDev d = p->d;
+            d.defer_compact = 1;
+            p->selects_since_compact++;
+            KB_CUDA(launch_pdl(3, k_pool_expand_select, dim3(pool_blocks(p)), dim3(32 * WARPS_PER_BLOCK), 0, st, d, (const float*)p->policy_dev,
+                               (const float*)p->value_dev, 1, 0, legal ? 1 : 0, planes, (Pos*)nullptr));
+        } else {
+            KB_CUDA(launch_pdl(2, k_pool_expand, dim3(pool_blocks(p)), dim3(32 * WARPS_PER_BLOCK), 0, st, p->d, (const float*)p->policy_dev,
+                               (const float*)p->value_dev, 1, 0, legal ? 1 : 0));
+        }
+        have_leaf = fuse;
         if (timed) KB_CUDA(cudaEventRecord(p->evs[k][3], st));
-        p->launches += 2 + (unsigned long long)net_launches_per_forward(net);
+        p->launches += 1 + (unsigned long long)net_launches_per_forward(net);
     }
     KB_CUDA(cudaEventRecord(p->ev[5], st));
     r = pool_check(p, true);
