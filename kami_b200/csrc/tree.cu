@@ -548,7 +548,8 @@ __device__ bool push_once(const PoolDev& P, int t, int action) {
     // The reserve must also cover what the batched loops allocate between the flag and the deferred collector's next run:
     // COMPACT_PERIOD selects with up to MAX_MOVES children each (tiny node budgets used to overflow here: 6 x 64 = 384
     // nodes were less than eight expansions of ~50 children).
-    u32 reserve = P.cfg.selfplay_nodes > 0 ? (u32)P.cfg.selfplay_nodes * 64u : 0u;
+    // (single-tree protocol, selfplay_nodes == 0: the caller's visit budget is unknown, half the arena is kept free)
+    u32 reserve = P.cfg.selfplay_nodes > 0 ? (u32)P.cfg.selfplay_nodes * 64u : P.cap / 2;
     if (reserve < (u32)(COMPACT_PERIOD + 2) * MAX_MOVES) reserve = (u32)(COMPACT_PERIOD + 2) * MAX_MOVES;
     if (reserve > P.cap / 2) reserve = P.cap / 2;
     if (c.alloc + reserve > P.cap && !P.defer_compact) compact_into_other_space(P, t, keep);
