@@ -35,7 +35,7 @@ TREES_PER_GPU = 1024
 FILTERS, RESIDUALS = 64, 2          # options.def.yml:29,53
 SELFPLAY_NODES = 1024               # options.def.yml selfplay_nodes
 NODE_CAPACITY = 1 << 19  # 2 x 10 MB per tree: the copying collector runs about once per 40 moves
-TOWER64_DRAM_BYTES_PER_LAUNCH = 12606720  # profiles/r01_ncu_summary_v2.txt
+TOWER64_DRAM_BYTES_PER_LAUNCH = 12861440  # profiles/r01_ncu_summary_v3.txt
 PREROLL_STEPS = 1536                # untimed: grows the synthetic trees to steady state (first moves made)
 METRIC = "selfplay_nn_evals_per_sec"
 UNIT = "evals/s"
@@ -412,6 +412,8 @@ def encoder_leg(api, L, pool, hbm_peak, peak_kind, n=131072, reps=10):
     api._ck(L.kb_dev_upload(dpos, pos.ctypes.data_as(C.c_void_p), pos.nbytes))
     out = {"positions": n, "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_kind": peak_kind}
     ms = C.c_float()
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch at n = 131072 (ncu --set full, profiles/r01_ncu_summary_v3.txt)
+    ncu_traffic = {"k_encode_f32": 10495232 + 951133184, "k_encode_tall": 10511872 + 510364672}
     for name, fn, nbytes in (("k_encode_f32", lambda: L.kb_encode_planes_dev(dpos, n, dobs), 64 + 7680),
                              ("k_encode_tall", lambda: L.kb_encode_planes_bf16_dev(dpos, n, dtall), 64 + 4096)):
         for _ in range(3):
@@ -423,7 +425,8 @@ def encoder_leg(api, L, pool, hbm_peak, peak_kind, n=131072, reps=10):
         L.kb_timer_stop(C.byref(ms))
         t = ms.value * 1e-3 / reps
         out[name] = {"us_per_launch": t * 1e6, "positions_per_sec": n / t, "algorithmic_bytes_per_position": nbytes,
-                     "achieved": n * nbytes / t / 1e9, "frac": n * nbytes / t / 1e9 / hbm_peak}
+                     "achieved": n * nbytes / t / 1e9, "frac": n * nbytes / t / 1e9 / hbm_peak,
+                     "traffic": ncu_traffic[name] if n == 131072 else None}
     for p in (dpos, dobs, dtall):
         L.kb_dev_free(p)
     return out
@@ -501,12 +504,12 @@ def run_ours(args, rank, world, local, dist):
     # roofline of the dominant kernel of the step (timed live with CUDA events inside kb_pool_step)
     t_f, h_f = net.flops()
     phases = {"select+encode": ph["select"], "tower+heads": ph["tower"], "expand+backup": ph["expand"]}
-    # dominant kernel of the step: k_tower64 (56 % of the step in the ncu launch list, profiles/r01_ncu_summary_v2.txt)
+    # dominant kernel of the step: k_tower64 (58 % of the step in the ncu launch list, profiles/r01_ncu_summary_v3.txt)
     achieved = (t_f + h_f) * TREES_PER_GPU / (ph["tower"] * 1e-3) / 1e12
     roof = {"kernel": "k_tower64 (one fused tcgen05 launch: %dx%d tower + policy/value heads + legal-move softmax)" % (RESIDUALS, FILTERS),
             "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one k_tower64 launch at 1024 boards, from the
-            # ncu --set full capture summarised in profiles/r01_ncu_summary_v2.txt (12.607 MB read: 147 input
+            # ncu --set full capture summarised in profiles/r01_ncu_summary_v3.txt (12.861 MB read: 147 input
             # slabs of 80 KB + weights)
             "traffic": TOWER64_DRAM_BYTES_PER_LAUNCH if TREES_PER_GPU == 1024 else None,
             "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst",
@@ -516,7 +519,7 @@ def run_ours(args, rank, world, local, dist):
     per_step += 3904.0 * TREES_PER_GPU
     dur = (ph["select"] + ph["expand"]) * 1e-3
     roof_tree = {"kernel": "k_pool_select + k_pool_expand", "bound": "hbm", "achieved": per_step / dur / 1e9, "peak": hbm_peak,
-                 "unit": "GB/s", "frac": per_step / dur / 1e9 / hbm_peak, "traffic": 2369024 + 13312 + 2436864,
+                 "unit": "GB/s", "frac": per_step / dur / 1e9 / hbm_peak, "traffic": 2318592 + 1124096,
                  "traffic_unit": "bytes/step (ncu, select + expand)", "peak_kind": peak_kind,
                  "algorithmic": "12 B x children scanned + 16 B x path nodes + 16 B x children created + 3904 B planes per leaf"}
 
