@@ -591,15 +591,13 @@ KB_HD u64 attack_spans(u64 pawns, int col) {
     u64 f = front_spans(pawns, col);
     return ((f << 1) & ~FILE_A) | ((f >> 1) & ~FILE_H);
 }
-KB_HD u64 isolated_pawns(u64 pawns) {  // board.c:281-294: only LATER (higher-square) pawns are tested
-    u64 out = 0, rest = pawns;
-    while (rest) {
-        int s = pop_lsb(rest);
-        int f = s & 7;
-        u64 nb = (f > 0 ? FILE_A << (f - 1) : 0) | (f < 7 ? FILE_A << (f + 1) : 0);
-        if (!(nb & rest)) out |= bit(s);
-    }
-    return out;
+// board.c:281-294 walks the pawns from the lowest square up and tests each one only against the pawns that come LATER
+// in that walk: a pawn counts as isolated unless some pawn on an adjacent file stands on a higher square -- a higher rank,
+// or the same rank one file to the right.  Closed form of exactly that set (no per-pawn loop):
+KB_HD u64 isolated_pawns(u64 pawns) {
+    const u64 below = south_fill(pawns >> 8);  // squares strictly below some pawn of the same file
+    const u64 has_higher_neighbour = ((below << 1) & ~FILE_A) | ((below >> 1) & ~FILE_H) | ((pawns >> 1) & ~FILE_H);
+    return pawns & ~has_higher_neighbour;
 }
 KB_HD u64 backward_pawns(u64 own_pawns, u64 opp_pawns, int col) {  // board.c:296-309
     u64 stops = shl(own_pawns, col == WHITE ? 8 : -8);
@@ -682,18 +680,19 @@ KB_HDN int static_eval(const Pos& p, const int* guard_mg = nullptr, const int* g
         mg -= d * 15;
         eg -= d * 15;
     }
-    for (int f = 0; f < 8; ++f) {
-        const u64 file = FILE_A << f, fp = p.pc[PAWN] & file;
-        const u64 nxt = file << 1;  // the mask is advanced before the open-file test uses it (:1227-1232)
-        if (!fp) {
-            int r = popc(nxt & p.pc[ROOK] & W) - popc(nxt & p.pc[ROOK] & B);
-            int q = popc(nxt & p.pc[QUEEN] & W) - popc(nxt & p.pc[QUEEN] & B);
-            mg += (r + q) * 5;
-            eg += (r + q) * 5;
-        }
-        const int nw = popc(fp & W), nb = popc(fp & B);
-        mg += (nw - 1) * -10 - (nb - 1) * -10;
-        eg += (nw - 1) * -20 - (nb - 1) * -20;
+    {   // position.c:1221-1245, one pass over the files in the reference.  (a) Open files: for every file without pawns the
+        // rooks and queens on the NEXT file mask are counted -- the mask is advanced before the test uses it (:1227-1232),
+        // and advancing the h-file mask gives a2..a8.  All files at once: the pawnless files shifted left by one bit.
+        const u64 with_pawns = north_fill(p.pc[PAWN]) | south_fill(p.pc[PAWN]);
+        const u64 nxt = ~with_pawns << 1;
+        const int r = popc(nxt & p.pc[ROOK] & W) - popc(nxt & p.pc[ROOK] & B);
+        const int q = popc(nxt & p.pc[QUEEN] & W) - popc(nxt & p.pc[QUEEN] & B);
+        mg += (r + q) * 5;
+        eg += (r + q) * 5;
+        // (b) Doubled pawns: sum over the 8 files of (nw_f - 1) * -10 - (nb_f - 1) * -10; the -1 terms cancel.
+        const int dp = popc(bp) - popc(wp);
+        mg += dp * 10;
+        eg += dp * 20;
     }
     const int wc = popc((((wp & ~FILE_A) << 7) | ((wp & ~FILE_H) << 9)) & wp);
     const int bc = popc((((bp & ~FILE_A) << 7) | ((wp & ~FILE_H) << 9)) & wp);  // (:1259) mixes colours
