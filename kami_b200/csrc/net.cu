@@ -1014,16 +1014,20 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 KB_STAMP();
                 if (l == P.tower_layers) epi_bar();  // every warp finished reading X for the value head
                 const int ncg = L.n / 16;
-                const int cg0 = half == 0 ? 0 : (ncg + 1) / 2, cg1 = half == 0 ? (ncg + 1) / 2 : ncg;
+                // The two warps of a lane quarter split the TILES (even / odd), not the columns: the same instruction count
+                // per warp, but half as many dependent TMEM-load -> convert -> store chains for the 64-column tower layers.
 #pragma unroll 1
-                for (int mt = 0; mt < 4; ++mt) {
+                for (int mt = half; mt < 4; mt += 2) {
                     const int r = 32 * q + lane;
                     const int R = 16 * mt + (r >> 3), x = r & 7;
                     const int slot = (R - 1) / 9, y = (R - 1) - slot * 9;
                     const bool valid = R >= 1 && y < 8 && slot < NB;
                     const int px = R * TALL_PITCH + 1 + x;
                     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + mt * L.n;
-                    // up to 4 column groups (64 fp32 columns) per warp and tile: issue every TMEM load, wait once
+#pragma unroll 1
+                  for (int cg0 = 0; cg0 < ncg; cg0 += 4) {
+                    const int cg1 = cg0 + 4 < ncg ? cg0 + 4 : ncg;
+                    // up to 4 column groups (64 fp32 columns) per round: issue every TMEM load, wait once
                     uint32_t v[4][16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
@@ -1078,6 +1082,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                             }
                         }
                     }
+                  }
                 }
                 fence_async_smem();       // generic-proxy smem writes -> visible to tcgen05.mma
                 ptx::tc_fence_before();
