@@ -1,0 +1,22 @@
+import sys, ctypes as C
+sys.path.insert(0,'tests'); sys.path.insert(0,'oracle'); sys.path.insert(0,'.')
+import numpy as np, kami_b200, nn_oracle as NO, harness as H
+from kami_b200 import api
+api.init(0); L=kami_b200.lib()
+net = kami_b200.NN(64,2); net.load_blob(NO.pack_blob(NO.init_params(64,2,seed=1),64,2))
+kw = dict(noise_weight=0.05, selfplay_nodes=1024, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5, alpha_cutoff=20, draw_value_pct=50, **H.DEF_YML)
+pool = kami_b200.TreePool(1024, 1<<19, api.tree_cfg(seed=1000, **kw))
+pool.step(net, 600)
+L.kb_net_debug_timestamps(net.h, 1, None, 0, None)
+names=["zero-fill"]+sum([["L%d wait acc"%l,"L%d epilogue"%l] for l in range(7)],[])+["value+bar","softmax"]
+acc=None
+for rep in range(20):
+    pool.step(net, 1)
+    ts=(C.c_longlong*64)(); n=C.c_int()
+    L.kb_net_debug_timestamps(net.h, 1, ts, 64, C.byref(n))
+    t=np.array(ts[:n.value]); d=np.diff(t)
+    acc = d if acc is None else acc+d
+acc=acc/20
+print("legal mode, mean of 20 steps, total cycles", acc.sum())
+for nm,x in zip(names,acc): print("%-16s %7d"%(nm,x))
+ph=pool.phase_ms(); print(ph)
