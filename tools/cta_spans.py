@@ -1,10 +1,10 @@
 import sys, ctypes as C
-sys.path.insert(0,'tests'); sys.path.insert(0,'oracle'); sys.path.insert(0,'.')
-import numpy as np, kami_b200, nn_oracle as NO, harness as H
+sys.path.insert(0,'.')
+import numpy as np, kami_b200, bench
 from kami_b200 import api
 api.init(0); L=kami_b200.lib()
-net = kami_b200.NN(64,2); net.load_blob(NO.pack_blob(NO.init_params(64,2,seed=1),64,2))
-kw = dict(noise_weight=0.05, selfplay_nodes=1024, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5, alpha_cutoff=20, draw_value_pct=50, **H.DEF_YML)
+net = kami_b200.NN(64,2); net.load_blob(bench.random_blob(64,2,seed=1))
+kw = dict(noise_weight=0.05, selfplay_nodes=1024, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5, alpha_cutoff=20, draw_value_pct=50, **kami_b200.DEF_YML)
 pool = kami_b200.TreePool(1024, 1<<19, api.tree_cfg(seed=1000, **kw))
 pool.step(net, 600)
 L.kb_net_debug_timestamps(net.h, 1, None, 0, None)
