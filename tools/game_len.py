@@ -1,6 +1,6 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, 'tests'); sys.path.insert(0, 'oracle')
+
 import numpy as np, kami_b200, bench
 from kami_b200 import api
 api.init(0)
