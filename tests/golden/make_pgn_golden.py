@@ -38,6 +38,11 @@ def main(n_games=160, keep=16):
     # shortest of the rest
     games.sort(key=lambda r: ("mated" not in r["reason"], "=" not in r["pgn"], "O-O" not in r["pgn"], len(r["actions"])))
     out = games[:keep]
+    if "--check" in sys.argv:  # tests/test_pgn_golden.py: the committed fixture is what the reference prints today
+        have = json.load(open(os.path.join(HERE, "pgn_games.json")))
+        assert have == out, "tests/golden/pgn_games.json differs from the reference's output"
+        print("pgn fixture matches the compiled reference:", len(out), "games")
+        return
     json.dump(out, open(os.path.join(HERE, "pgn_games.json"), "w"))
     print(len(games), "games without a Q3 event of", n_games)
     for r in out:
