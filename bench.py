@@ -495,8 +495,13 @@ def run_ours(args, rank, world, local, dist):
     ms = timed_steps(lambda k: pool.step(net, k), args.steps)
     clocks = sampler.stop()
     st = pool.stats()
-    ph = pool.phase_ms()
     evals_local = float(st["evals"])
+    # phase times (and the roofline's kernel duration): a separate short PROFILED call -- the timed run above records
+    # no events and fuses expand + select everywhere (kb_pool_set_profiling is opt-in)
+    pool.set_profiling(True)
+    pool.step(net, 64)
+    ph = pool.phase_ms()
+    pool.set_profiling(False)
     evals = reduce_sum(dist, local, evals_local)
     moves = reduce_sum(dist, local, float(st["moves"]))
     value = evals / (ms * 1e-3)
@@ -627,7 +632,7 @@ def run_ours(args, rank, world, local, dist):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(),
         "positions_per_sec": moves / (ms * 1e-3),
-        "phase_ms_mean_of_32_sampled_steps": phases,
+        "phase_ms_profiled_call_mean_of_32_steps": phases,
         "roofline": roof,
         "roofline_tree_kernels": roof_tree,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

@@ -53,8 +53,15 @@ typedef struct kb_position {
     uint8_t pad;
 } kb_position;
 
-/* ---- library -------------------------------------------------------------------------- */
-int kb_init(int device);          /* bind the calling process to `device`, upload tables */
+/* ---- library --------------------------------------------------------------------------
+ * Threading (reference: selfplay.cpp:25-31 inference / training threads over one NN, nn.cpp:164-168): every host
+ * thread has its own CUDA stream per device inside the library; kb_pool / kb_env / kb_trainer are owned by one
+ * thread at a time like the reference's MCTS / Env; a kb_net may be used from any number of threads at once
+ * (kb_net_infer, kb_pool_step, ... hold its weights under a shared lock, kb_net_load_blob takes it exclusively).
+ * Devices: kb_init(d) binds the CALLING THREAD to device d; objects remember the device they were created on and
+ * their entry points run there, so one process can drive every GPU of a box with one host thread per GPU. */
+int kb_init(int device);          /* bind the calling thread to `device` (first call per device uploads tables); < 0: default */
+int kb_current_device(void);      /* device the calling thread is bound to, -1 before kb_init */
 const char* kb_last_error(void);
 int kb_device_count(void);
 int kb_device_name(char* out, int cap);
@@ -157,6 +164,10 @@ int kb_pool_select(kb_pool* p);                 /* every tree: one leaf (termina
 int kb_pool_leaf_positions(kb_pool* p, kb_position* out /*[n_trees] host*/);
 int kb_pool_expand(kb_pool* p, const float* policy /*[n][4672] host*/, const float* value /*[n] host*/, int disable_bootstrap);
 int kb_pool_expand_dev(kb_pool* p, const float* policy_dev, const float* value_dev, int disable_bootstrap);
+/* compact forms of the same exchange: every pending leaf's Env::actions() list (row pitch 128, -1 padded) out;
+ * prior[t][i] = (unnormalised) policy mass of tree t's i-th legal action + value[t] in (mcts.h:257-327) */
+int kb_pool_leaf_actions(kb_pool* p, int32_t* actions /*[n][128] host*/, int32_t* counts /*[n] host*/);
+int kb_pool_expand_compact(kb_pool* p, const float* prior /*[n][128] host*/, const float* value /*[n] host*/, int disable_bootstrap);
 /* the whole loop of selfplay.cpp:113-200: select -> encode -> tower+heads -> expand/backup, `iters` times */
 int kb_pool_step(kb_pool* p, kb_net* net, int iters);
 /* same, but every iteration's leaf planes round-trip through host memory like the reference
@@ -166,6 +177,18 @@ int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, flo
  * inference_threads (selfplay.cpp:25-31): each group has its own NN::infer batch (so Q1's value indexing is per
  * group) and its own streams, so one group's transfers overlap another's compute.  0 = default (4), max 8. */
 int kb_pool_set_hostio_groups(kb_pool* p, int groups);
+/* kb_pool_step_hostio with the compact forms on the wire: 80-byte leaf positions (instead of [1920] fp32 observation
+ * rows) out and back in, [128] legal-move priors (instead of [4672] policy rows) + value out and back in */
+int kb_pool_step_hostio_compact(kb_pool* p, kb_net* net, int iters, kb_position* leaf_host /*[n]*/, float* prior_host /*[n][128]*/,
+                                float* value_host /*[n]*/);
+/* kb_pool_step serves the trees as `groups` independent pipelines (the analogue of inference_threads, selfplay.cpp:25-31:
+ * own trees, own NN batch -- Q1's value indexing is per group -- own stream); 0 = default (KB_STEP_GROUPS or 1), max 8 */
+int kb_pool_set_step_groups(kb_pool* p, int groups);
+/* phase timing of kb_pool_step (kb_pool_last_phase_ms) is opt-in: when on, up to 32 iterations of a call are bracketed
+ * by CUDA events and not fused with their neighbours; off (default) the call records nothing and always fuses */
+int kb_pool_set_profiling(kb_pool* p, int on);
+/* flush_old_trees (selfplay.cpp:61,119-131): MCTS::reset on every tree, partial trajectories dropped */
+int kb_pool_flush_trees(kb_pool* p);
 
 typedef struct kb_pool_stats {
     uint64_t evals;          /* NN evaluations (leaves expanded) */
@@ -210,6 +233,9 @@ int kb_dev_download(void* dst_host, const void* src_dev, size_t bytes);
 int kb_dev_sync(void);
 int kb_host_alloc_pinned(void** out, size_t bytes);
 int kb_host_free_pinned(void* ptr);
+/* pin a caller-owned host buffer (cudaHostRegister) so the host-pointer entry points DMA straight from / into it */
+int kb_host_register(void* ptr, size_t bytes);
+int kb_host_unregister(void* ptr);
 /* CUDA-event timer and L2 flush on the library's stream (bench.py) */
 int kb_timer_start(void);
 int kb_timer_stop(float* ms);

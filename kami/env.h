@@ -80,6 +80,8 @@ class Env {
         kb_check(kb_env_reset(h));
         curturn = 1.0f;
         history.clear();
+        actions_utd = false;  // (the reference's copy takes o.actions_utd / o.cur_actions; recomputing is equivalent)
+        cur_actions.clear();
         for (ncMove mv : o.history) {
             int a = 0;
             kb_check(kb_env_encode(h, mv, &a));

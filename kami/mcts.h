@@ -142,7 +142,9 @@ class MCTS {
     int pick(float alpha = 0.0f) {
         if (!root->children.size()) throw std::runtime_error("no children to pick from");
         int action = -1;
-        double u = (double)rand() / (double)RAND_MAX;  // mcts.h:173 (drawn even when alpha < 0.1: harmless superset)
+        // mcts.h:141-173: rand() is drawn on the temperature path only -- the greedy path must not advance the
+        // process-wide stream (evaluate.cpp:22 colours and ReplayBuffer::select_batch read it too)
+        const double u = alpha >= 0.1f ? (double)rand() / (double)RAND_MAX : 0.0;
         kb_check(kb_tree_pick(pool, slot, alpha, u, &action));
         return action;
     }

@@ -7,7 +7,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
+#include <condition_variable>
 #include <iostream>
+#include <mutex>
 #include <random>
 #include <shared_mutex>
 #include <stdexcept>
@@ -18,12 +20,45 @@
 #include "../options.h"
 
 namespace kami {
+// NN::mut of the reference is a std::shared_mutex (nn.h:47).  Here the inference threads hold it shared for a whole
+// device-resident step at a time, i.e. almost always, and glibc's rwlock prefers readers: read() / train() could wait
+// forever.  Same interface (usable with std::shared_lock / std::unique_lock), but a waiting writer stops new readers.
+class WriterFirstSharedMutex {
+    std::mutex m;
+    std::condition_variable cv;
+    int readers = 0, writers_waiting = 0;
+    bool writing = false;
+
+   public:
+    void lock_shared() {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [&] { return !writing && writers_waiting == 0; });
+        ++readers;
+    }
+    void unlock_shared() {
+        std::unique_lock<std::mutex> g(m);
+        if (--readers == 0) cv.notify_all();
+    }
+    void lock() {
+        std::unique_lock<std::mutex> g(m);
+        ++writers_waiting;
+        cv.wait(g, [&] { return !writing && readers == 0; });
+        --writers_waiting;
+        writing = true;
+    }
+    void unlock() {
+        std::unique_lock<std::mutex> g(m);
+        writing = false;
+        cv.notify_all();
+    }
+};
+
 class NN {
    private:
     kb_net* net = nullptr;
     int width, height, features, psize;
     int filters, residuals;
-    std::shared_mutex mut;
+    WriterFirstSharedMutex mut;
     int generation = 0;
     std::vector<float> blob;
 
@@ -79,7 +114,7 @@ class NN {
         check(kb_net_load_blob(net, blob.data(), blob.size()));
     }
     NN(NN* other) : width(other->width), height(other->height), features(other->features), psize(other->psize) {
-        std::shared_lock<std::shared_mutex> g(other->mut);
+        std::shared_lock<WriterFirstSharedMutex> g(other->mut);
         filters = other->filters;
         residuals = other->residuals;
         generation = other->generation;
@@ -92,7 +127,7 @@ class NN {
     NN& operator=(const NN&) = delete;
 
     int get_generation() {
-        std::shared_lock<std::shared_mutex> g(mut);
+        std::shared_lock<WriterFirstSharedMutex> g(mut);
         return generation;
     }
     int get_device() { return 0; }
@@ -103,8 +138,17 @@ class NN {
 
     // nn.cpp:155-187: host buffers in and out, NaN -> runtime_error, value[i] = vh.flat[i]
     void infer(float* input, int batch, float* policy, float* value) {
-        std::shared_lock<std::shared_mutex> g(mut);
+        std::shared_lock<WriterFirstSharedMutex> g(mut);
         int rc = kb_net_infer(net, input, batch, policy, value);
+        if (rc == KB_ERR_NAN) throw std::runtime_error("inference policy output contains NaN");
+        check(rc);
+    }
+    // The device-resident form of the inference loop's NN::infer call (selfplay.cpp:196): `iters` rounds of
+    // select -> tower -> expand on a pool, under the same shared lock NN::infer takes (nn.cpp:166), so read() / train()
+    // never swap the weights under a running step.
+    void pool_step(kb_pool* pool, int iters) {
+        std::shared_lock<WriterFirstSharedMutex> g(mut);
+        int rc = kb_pool_step(pool, net, iters);
         if (rc == KB_ERR_NAN) throw std::runtime_error("inference policy output contains NaN");
         check(rc);
     }
@@ -115,7 +159,7 @@ class NN {
     // batch's rows (nn.cpp:278-298); the batches themselves are copied to the device as on the reference's CUDA
     // path (its CPU path aliases one stack buffer for every stored batch, nn.cpp:300-316).
     void train(int trajectories, float* inputs, float* obs_p, float* obs_v, bool detect_anomaly = false) {
-        std::unique_lock<std::shared_mutex> g(mut);
+        std::unique_lock<WriterFirstSharedMutex> g(mut);
         const float lr = (float)options::getInt("training_mlr", 5) / 1000.0f;
         const int epochs = options::getInt("training_epochs", 8);
         const int tbatch = options::getInt("training_batchsize", 8);
@@ -172,7 +216,7 @@ class NN {
     // Checkpoint = "KB20" + filters + residuals + generation + fp32 blob.  (The reference writes a
     // torch archive, nn.cpp:189-222; archive interop is SURVEY.md 8(f) #3.)
     void write(std::string path) {
-        std::shared_lock<std::shared_mutex> g(mut);
+        std::shared_lock<WriterFirstSharedMutex> g(mut);
         std::ofstream f(path, std::ios::binary);
         if (!f) throw std::runtime_error("couldn't open " + path + " for writing");
         int32_t hdr[4] = {0x3032424B, filters, residuals, generation};
@@ -181,7 +225,7 @@ class NN {
         std::cout << "Saved model to " << path << std::endl;
     }
     void read(std::string path) {
-        std::unique_lock<std::shared_mutex> g(mut);
+        std::unique_lock<WriterFirstSharedMutex> g(mut);
         std::ifstream f(path, std::ios::binary);
         int32_t hdr[4];
         if (!f || !f.read((char*)hdr, sizeof(hdr)) || hdr[0] != 0x3032424B || hdr[1] != filters || hdr[2] != residuals)
@@ -194,7 +238,7 @@ class NN {
     }
     // explicit weight loading from a flat blob (the oracle's exchange format)
     void load_blob(const float* data, size_t n) {
-        std::unique_lock<std::shared_mutex> g(mut);
+        std::unique_lock<WriterFirstSharedMutex> g(mut);
         check(kb_net_load_blob(net, data, n));
         blob.assign(data, data + n);
     }

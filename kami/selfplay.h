@@ -106,21 +106,36 @@ class Selfplay {
         cfg.draw_value_pct = options::getInt("draw_value_pct", 50);
         kb_pool* pool = nullptr;
         kb_check(kb_pool_create(&pool, ibatch, options::getInt("b200_node_capacity", 1 << 18), &cfg));
-        std::vector<float> obs((size_t)64 * OBSIZE), pi((size_t)64 * PSIZE), z(64);
+        const int DRAIN = 256;  // replay rows fetched per call (one device -> host copy per call)
+        std::vector<float> obs((size_t)DRAIN * OBSIZE), pi((size_t)DRAIN * PSIZE), z(DRAIN);
+        const bool flush_old_trees = options::getInt("flush_old_trees", 1) != 0;  // selfplay.cpp:61
+        int source_generation = model->get_generation();                          // selfplay.cpp:103
+        long long flushed = 0;
+        const int iters_per_call = options::getInt("b200_iters_per_call", 64);
         std::vector<int32_t> game_actions(4096);
         bool game_requested = false;
         auto partial = partial_trajectories.begin();
         std::advance(partial, id);
         while (status.code() == RUNNING) {
-            kb_check(kb_pool_step(pool, model->handle(), 64));
+            // selfplay.cpp:119-131: trees searched with an older generation are replaced and their partial trajectories
+            // dropped (all of a thread's trees share one source generation here: they are stepped together)
+            const int gen = model->get_generation();
+            if (flush_old_trees && source_generation < gen) {
+                kb_pool_stats before;
+                kb_check(kb_pool_get_stats(pool, &before));
+                flushed = (long long)(before.moves - before.samples);  // every partial trajectory is dropped (:126-127)
+                kb_check(kb_pool_flush_trees(pool));
+                source_generation = gen;
+            }
+            model->pool_step(pool, iters_per_call);
             kb_pool_stats st;
             kb_check(kb_pool_get_stats(pool, &st));
-            *partial = (int)(st.moves - st.samples);  // positions recorded in games still being played (selfplay.cpp:150-151)
+            *partial = (int)((long long)(st.moves - st.samples) - flushed);  // positions recorded in games still being played (selfplay.cpp:150-151)
             int m = 0;
             do {
-                kb_check(kb_pool_drain_samples(pool, 64, obs.data(), pi.data(), z.data(), &m));
+                kb_check(kb_pool_drain_samples(pool, DRAIN, obs.data(), pi.data(), z.data(), &m));
                 for (int i = 0; i < m; ++i) replay_buffer.add(&obs[(size_t)i * OBSIZE], &pi[(size_t)i * PSIZE], z[i]);
-            } while (m == 64);
+            } while (m == DRAIN);
             // selfplay.cpp:167-171: hand the next finished game to get_next_pgn().  The device keeps the moves of the
             // game; its movetext is written by replaying them on an Env.
             if (!game_requested && wants_pgn.load()) {

@@ -143,7 +143,16 @@ _SIGS = {
     "kb_pool_leaf_positions": (C.c_int, [_P, _P]),
     "kb_pool_expand": (C.c_int, [_P, _f32p, _f32p, C.c_int]),
     "kb_pool_expand_dev": (C.c_int, [_P, _P, _P, C.c_int]),
+    "kb_pool_leaf_actions": (C.c_int, [_P, _i32p, _i32p]),
+    "kb_pool_expand_compact": (C.c_int, [_P, _f32p, _f32p, C.c_int]),
     "kb_pool_step": (C.c_int, [_P, _P, C.c_int]),
+    "kb_pool_step_hostio_compact": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "kb_pool_set_step_groups": (C.c_int, [_P, C.c_int]),
+    "kb_pool_set_profiling": (C.c_int, [_P, C.c_int]),
+    "kb_pool_flush_trees": (C.c_int, [_P]),
+    "kb_current_device": (C.c_int, []),
+    "kb_host_register": (C.c_int, [_P, C.c_size_t]),
+    "kb_host_unregister": (C.c_int, [_P]),
     "kb_pool_step_hostio": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "kb_pool_get_stats": (C.c_int, [_P, C.POINTER(PoolStats)]),
     "kb_pool_reset_stats": (C.c_int, [_P]),
@@ -507,6 +516,35 @@ class TreePool:
 
     def step_hostio(self, net, iters, obs, policy, value):
         _ck(self.L.kb_pool_step_hostio(self.h, net.h, iters, _vp(obs), _vp(policy), _vp(value)))
+
+    def step_hostio_compact(self, net, iters, leaves, prior, value):
+        """step_hostio with 80-byte leaf positions and [128] legal-move priors on the wire."""
+        _ck(self.L.kb_pool_step_hostio_compact(self.h, net.h, iters, _vp(leaves), _vp(prior), _vp(value)))
+
+    def set_step_groups(self, groups):
+        """step(): independent groups of trees, each with its own NN batch and stream (0 = default)."""
+        _ck(self.L.kb_pool_set_step_groups(self.h, int(groups)))
+
+    def set_profiling(self, on):
+        """Phase timing of step() (phase_ms) is opt-in; off, step() records nothing and always fuses expand + select."""
+        _ck(self.L.kb_pool_set_profiling(self.h, int(bool(on))))
+
+    def flush_trees(self):
+        """flush_old_trees (selfplay.cpp:119-131): every tree back to the start position, partial trajectories dropped."""
+        _ck(self.L.kb_pool_flush_trees(self.h))
+
+    def leaf_actions(self):
+        """Legal actions of every pending leaf in Env::actions() order: ([n,128] int32, -1 padded; [n] counts)."""
+        a = np.zeros((self.n, MAX_ACTIONS), np.int32)
+        c = np.zeros(self.n, np.int32)
+        _ck(self.L.kb_pool_leaf_actions(self.h, _ip(a), _ip(c)))
+        return a, c
+
+    def expand_compact(self, prior, value, disable_bootstrap=False):
+        prior = np.ascontiguousarray(prior, np.float32)
+        value = np.ascontiguousarray(value, np.float32)
+        assert prior.size == self.n * MAX_ACTIONS and value.size == self.n
+        _ck(self.L.kb_pool_expand_compact(self.h, _fp(prior), _fp(value), int(disable_bootstrap)))
 
     def stats(self):
         s = PoolStats()

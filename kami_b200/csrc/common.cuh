@@ -10,9 +10,12 @@
 namespace kb {
 
 void set_error(const char* fmt, ...);
-cudaStream_t main_stream();
+cudaStream_t main_stream();  // the CALLING THREAD's stream on its current device (lib.cu: threading model)
 int sm_count();
 bool initialized();
+int current_device();
+int bind_device(int device);      // switch the calling thread to an initialised device
+void adopt(cudaStream_t* last);   // object hand-over between host threads: wait for the stream that last touched it
 
 #define KB_CUDA(expr)                                                                             \
     do {                                                                                          \
@@ -54,6 +57,14 @@ inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, di
             int _r = kb_init(-1);                                            \
             if (_r != KB_OK) return _r;                                      \
         }                                                                    \
+    } while (0)
+
+// entry points that take an object: run on the object's device, ordered after whatever last touched it
+#define KB_BIND(obj)                                   \
+    do {                                               \
+        int _b = kb::bind_device((obj)->device);       \
+        if (_b != KB_OK) return _b;                    \
+        kb::adopt(&(obj)->last_stream);                \
     } while (0)
 
 #define KB_ARG(cond, msg)                     \

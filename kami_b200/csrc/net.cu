@@ -15,6 +15,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -1373,18 +1375,55 @@ uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
 
 }  // namespace
 
+// Shared / exclusive lock that prefers writers: inference threads hold the weights shared almost all the time (a
+// kb_pool_step call is one long shared section), so a reader-preferring lock (glibc's default rwlock behind
+// std::shared_mutex) could starve NN::read / NN::train's weight swap indefinitely.  A waiting writer stops new readers.
+class WeightLock {
+    std::mutex m;
+    std::condition_variable cv;
+    int readers = 0, writers_waiting = 0;
+    bool writing = false;
+
+   public:
+    void lock_shared() {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [&] { return !writing && writers_waiting == 0; });
+        ++readers;
+    }
+    void unlock_shared() {
+        std::unique_lock<std::mutex> g(m);
+        if (--readers == 0) cv.notify_all();
+    }
+    void lock() {
+        std::unique_lock<std::mutex> g(m);
+        ++writers_waiting;
+        cv.wait(g, [&] { return !writing && readers == 0; });
+        --writers_waiting;
+        writing = true;
+    }
+    void unlock() {
+        std::unique_lock<std::mutex> g(m);
+        writing = false;
+        cv.notify_all();
+    }
+};
+
+// One host-pointer inference call's private state: workspace + staging (device and pinned host)
+struct InferCtx {
+    kb::NetWs ws;
+    float *obs_dev = nullptr, *pol_dev = nullptr, *val_dev = nullptr;
+    float *obs_pin = nullptr, *pol_pin = nullptr, *val_pin = nullptr;
+    int stage_cap = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
 struct kb_net {
     int filters, residuals;
+    int device = 0;
     bool loaded = false;
     std::vector<Layer> layers;  // conv1, (res conv1, res conv2)*, policyconv, policyconv2
     float *wv = nullptr, *fct = nullptr, *fcb = nullptr;
     float bv = 0.0f;
-    int cap_boards = 0;
-    uint4 *P = nullptr, *X = nullptr, *Y = nullptr, *H = nullptr;
-    int* nan_flag = nullptr;
-    // staging for the host-pointer API
-    float *obs_dev = nullptr, *pol_dev = nullptr, *val_dev = nullptr;
-    int stage_cap = 0;
     int launches = 0;
     // fused single-kernel path (filters == 64)
     bool fused = false;
@@ -1392,35 +1431,53 @@ struct kb_net {
     uint4* fused_w = nullptr;
     float* fused_bias = nullptr;
     long long* ts_dev = nullptr;
-    float* logits_dev = nullptr;  // [cap][4672] scratch of the legal-gather mode (per-layer path)
-    int logits_cap = 0;
+    // weights: shared by every forward, exclusive for load_blob (nn.cpp:164-168, 206)
+    WeightLock mu;
+    // host-pointer calls (kb_net_infer / kb_net_forward_full): one private context per call in flight
+    std::mutex ctx_mu;
+    std::vector<InferCtx*> ctx_free;
+    InferCtx* dbg_ctx = nullptr;  // context of the last kb_net_forward_full (kb_net_debug_activation reads it)
 };
 
 namespace kb {
 
-int net_reserve(kb_net* net, int batch) {
-    if (batch <= net->cap_boards) return KB_OK;
-    cudaStreamSynchronize(main_stream());
-    cudaFree(net->P); cudaFree(net->X); cudaFree(net->Y); cudaFree(net->H);
-    const int fs = (net->filters + 63) / 64;
-    KB_CUDA(cudaMalloc(&net->P, act_bytes(batch, IN_SLABS)));
-    KB_CUDA(cudaMalloc(&net->X, act_bytes(batch, fs)));
-    KB_CUDA(cudaMalloc(&net->Y, act_bytes(batch, fs)));
-    KB_CUDA(cudaMalloc(&net->H, act_bytes(batch, 2)));
+void net_lock_shared(kb_net* net) { net->mu.lock_shared(); }
+void net_unlock_shared(kb_net* net) { net->mu.unlock_shared(); }
+int net_device(kb_net* net) { return net->device; }
+
+void ws_free(NetWs& ws) {
+    cudaFree(ws.P); cudaFree(ws.X); cudaFree(ws.Y); cudaFree(ws.H); cudaFree(ws.logits); cudaFree(ws.nan_flag);
+    ws = NetWs{};
+}
+
+int ws_reserve(NetWs& ws, kb_net* net, int batch, cudaStream_t st) {
+    const int fs = net->fused ? 0 : (net->filters + 63) / 64;  // the fused tower keeps its activations in shared memory
+    if (batch <= ws.cap_boards && fs <= ws.slabs) return KB_OK;
+    if (batch < ws.cap_boards) batch = ws.cap_boards;
+    cudaStreamSynchronize(st);  // the owner's stream is the only one that can still be using the old buffers
+    cudaFree(ws.P); cudaFree(ws.X); cudaFree(ws.Y); cudaFree(ws.H);
+    ws.P = ws.X = ws.Y = ws.H = nullptr;
+    ws.cap_boards = 0;
+    KB_CUDA(cudaMalloc(&ws.P, act_bytes(batch, IN_SLABS)));
     // pad pixels (and unused channel chunks) must read as zero forever; epilogues and encoders
     // only ever write the chunks of board pixels they own
-    KB_CUDA(cudaMemsetAsync(net->P, 0, act_bytes(batch, IN_SLABS), main_stream()));
-    KB_CUDA(cudaMemsetAsync(net->X, 0, act_bytes(batch, fs), main_stream()));
-    KB_CUDA(cudaMemsetAsync(net->Y, 0, act_bytes(batch, fs), main_stream()));
-    KB_CUDA(cudaMemsetAsync(net->H, 0, act_bytes(batch, 2), main_stream()));
-    if (!net->nan_flag) {
-        KB_CUDA(cudaMalloc(&net->nan_flag, sizeof(int)));
-        KB_CUDA(cudaMemsetAsync(net->nan_flag, 0, sizeof(int), main_stream()));
+    KB_CUDA(cudaMemsetAsync(ws.P, 0, act_bytes(batch, IN_SLABS), st));
+    if (fs) {
+        KB_CUDA(cudaMalloc(&ws.X, act_bytes(batch, fs)));
+        KB_CUDA(cudaMalloc(&ws.Y, act_bytes(batch, fs)));
+        KB_CUDA(cudaMalloc(&ws.H, act_bytes(batch, 2)));
+        KB_CUDA(cudaMemsetAsync(ws.X, 0, act_bytes(batch, fs), st));
+        KB_CUDA(cudaMemsetAsync(ws.Y, 0, act_bytes(batch, fs), st));
+        KB_CUDA(cudaMemsetAsync(ws.H, 0, act_bytes(batch, 2), st));
     }
-    net->cap_boards = batch;
+    if (!ws.nan_flag) {
+        KB_CUDA(cudaMalloc(&ws.nan_flag, sizeof(int)));
+        KB_CUDA(cudaMemsetAsync(ws.nan_flag, 0, sizeof(int), st));
+    }
+    ws.cap_boards = batch;
+    ws.slabs = fs;
     return KB_OK;
 }
-void* net_input_planes(kb_net* net) { return net->P; }
 int net_launches_per_forward(kb_net* net) { return net->fused ? 1 : (int)net->layers.size() + 2; }
 
 static long long* g_conv_ts = nullptr;  // profiling hook (kb_net_debug_timestamps)
@@ -1429,10 +1486,10 @@ static int g_conv_ts_slot = 0;          // 16 counters per launch, 8 launches ke
 template <int N_TILE>
 static int launch_conv(const ConvParams& p, cudaStream_t st) {
     using C = ConvCfg<N_TILE>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[16] = {};  // function attributes are per device
+    if (!configured[current_device() & 15]) {
         KB_CUDA(cudaFuncSetAttribute(k_conv<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        configured = true;
+        configured[current_device() & 15] = true;
     }
     const int grid = p.items < sm_count() ? p.items : sm_count();
     k_conv<N_TILE><<<grid, 256, C::SMEM, st>>>(p);
@@ -1443,10 +1500,10 @@ static int launch_conv(const ConvParams& p, cudaStream_t st) {
 template <int N_TILE>
 static int launch_conv2(const ConvParams& p, cudaStream_t st) {
     using C = Conv2Cfg<N_TILE>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[16] = {};
+    if (!configured[current_device() & 15]) {
         KB_CUDA(cudaFuncSetAttribute(k_conv2<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        configured = true;
+        configured[current_device() & 15] = true;
     }
     const int pairs = (p.items + 1) / 2, max_pairs = sm_count() / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
@@ -1498,19 +1555,19 @@ static int run_conv(const Layer& L, const uint4* in, uint4* out, const uint4* sk
     return KB_ERR_UNSUPPORTED;
 }
 
-static int net_stage_logits(kb_net* net, int batch, float** out) {
-    if (batch > net->logits_cap) {
-        cudaStreamSynchronize(main_stream());
-        cudaFree(net->logits_dev);
-        net->logits_dev = nullptr;
-        net->logits_cap = 0;
-        if (cudaMalloc(&net->logits_dev, sizeof(float) * KB_PSIZE * (size_t)batch) != cudaSuccess) {
+static int ws_stage_logits(NetWs& ws, int batch, float** out, cudaStream_t st) {
+    if (batch > ws.logits_cap) {
+        cudaStreamSynchronize(st);
+        cudaFree(ws.logits);
+        ws.logits = nullptr;
+        ws.logits_cap = 0;
+        if (cudaMalloc(&ws.logits, sizeof(float) * KB_PSIZE * (size_t)batch) != cudaSuccess) {
             set_error("out of device memory for the logits scratch");
             return 1;
         }
-        net->logits_cap = batch;
+        ws.logits_cap = batch;
     }
-    *out = net->logits_dev;
+    *out = ws.logits;
     return 0;
 }
 
@@ -1522,27 +1579,30 @@ struct LegalRef {
 };
 
 // item0: first item of the activation workspace (X / Y / H) this forward may use, so that forwards of disjoint
-// groups of boards can run concurrently on different streams (kb_pool_step_hostio)
-static int net_forward_impl(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, const LegalRef& lr,
-                            cudaStream_t st, int item0 = 0) {
+// groups of boards can run concurrently on different streams.  The workspace must already hold batch + item0 * NB
+// boards (ws_reserve by its owner, before any group is launched).
+static int net_forward_impl(kb_net* net, NetWs& ws, const void* planes, int batch, float* policy_dev, float* value256_dev, const LegalRef& lr,
+                            cudaStream_t st, int item0) {
     if (!net->loaded) {
         set_error("network weights not loaded");
         return KB_ERR_STATE;
     }
-    int r = net_reserve(net, batch + item0 * NB);
-    if (r) return r;
+    if (batch + item0 * NB > ws.cap_boards || (!net->fused && ws.slabs < (net->filters + 63) / 64)) {
+        set_error("activation workspace holds %d boards, forward needs %d", ws.cap_boards, batch + item0 * NB);
+        return KB_ERR_STATE;
+    }
     const uint4* in = reinterpret_cast<const uint4*>(planes);
     if (net->fused) {
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[16] = {};  // function attributes are per device
+        if (!configured[net->device]) {
             KB_CUDA(cudaFuncSetAttribute(k_tower64, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
-            configured = true;
+            configured[net->device] = true;
         }
         FusedParams fp = net->fp;
         fp.planes = in;
         fp.policy = policy_dev;
         fp.value256 = value256_dev;
-        fp.nan_flag = net->nan_flag;
+        fp.nan_flag = ws.nan_flag;
         fp.ts = net->ts_dev;
         fp.legal_act = lr.act;
         fp.legal_n = lr.nact;
@@ -1554,15 +1614,20 @@ static int net_forward_impl(kb_net* net, const void* planes, int batch, float* p
         KB_CUDA(launch_pdl(1, k_tower64, dim3(grid), dim3(384), FZ_SMEM, st, fp));
         return KB_OK;
     }
+    int r;
     float* logits = policy_dev;
     if (lr.act) {  // the dense logits are scratch in legal mode
-        if (net_stage_logits(net, batch, &logits)) return KB_ERR_CUDA;
+        if (item0 != 0) {
+            set_error("legal-gather forward of the per-layer path does not support workspace groups");
+            return KB_ERR_UNSUPPORTED;
+        }
+        if (ws_stage_logits(ws, batch, &logits, st)) return KB_ERR_CUDA;
     }
     size_t li = 0;
     const int fs = (net->filters + 63) / 64;
-    uint4* X = net->X + (size_t)item0 * fs * SLAB_U4;
-    uint4* Y = net->Y + (size_t)item0 * fs * SLAB_U4;
-    uint4* H = net->H + (size_t)item0 * 2 * SLAB_U4;
+    uint4* X = ws.X + (size_t)item0 * fs * SLAB_U4;
+    uint4* Y = ws.Y + (size_t)item0 * fs * SLAB_U4;
+    uint4* H = ws.H + (size_t)item0 * 2 * SLAB_U4;
     if ((r = run_conv(net->layers[li++], in, X, nullptr, nullptr, batch, st))) return r;
     for (int i = 0; i < net->residuals; ++i) {
         if ((r = run_conv(net->layers[li++], X, Y, nullptr, nullptr, batch, st))) return r;
@@ -1571,35 +1636,27 @@ static int net_forward_impl(kb_net* net, const void* planes, int batch, float* p
     if ((r = run_conv(net->layers[li++], X, H, nullptr, nullptr, batch, st))) return r;
     if ((r = run_conv(net->layers[li++], H, nullptr, nullptr, logits, batch, st))) return r;
     if (lr.act)
-        k_legal_prior<<<(batch + 7) / 8, 256, 0, st>>>(logits, batch, lr.act, lr.nact, lr.stride, lr.prior, net->nan_flag);
+        k_legal_prior<<<(batch + 7) / 8, 256, 0, st>>>(logits, batch, lr.act, lr.nact, lr.stride, lr.prior, ws.nan_flag);
     else
-        k_softmax<<<batch, 256, 0, st>>>(logits, batch, net->nan_flag);
+        k_softmax<<<batch, 256, 0, st>>>(logits, batch, ws.nan_flag);
     KB_CUDA(cudaGetLastError());
-    k_value_head<<<batch, 256, 0, st>>>(X, fs, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, net->nan_flag);
+    k_value_head<<<batch, 256, 0, st>>>(X, fs, batch, net->wv, net->bv, net->fct, net->fcb, value256_dev, ws.nan_flag);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
 
-int net_forward_async(kb_net* net, const void* planes, int batch, float* policy_dev, float* value256_dev, cudaStream_t st) {
-    return net_forward_impl(net, planes, batch, policy_dev, value256_dev, LegalRef{}, st);
+int net_forward_async(kb_net* net, NetWs& ws, const void* planes, int batch, float* policy_dev, float* value256_dev, cudaStream_t st, int item0) {
+    return net_forward_impl(net, ws, planes, batch, policy_dev, value256_dev, LegalRef{}, st, item0);
 }
 
-// forward of one group of boards on the workspace starting at item0; planes = net_input_planes(net) + item0 items
-int net_forward_group_async(kb_net* net, int item0, int batch, float* policy_dev, float* value256_dev, cudaStream_t st) {
-    int r = net_reserve(net, batch + item0 * NB);
-    if (r) return r;
-    return net_forward_impl(net, net->P + (size_t)item0 * IN_SLABS * SLAB_U4, batch, policy_dev, value256_dev, LegalRef{}, st, item0);
-}
-void* net_group_planes(kb_net* net, int item0) { return net->P + (size_t)item0 * IN_SLABS * SLAB_U4; }
-
-int net_forward_legal_async(kb_net* net, const void* planes, int batch, const void* act_base, const void* nact_base, size_t stride,
-                            float* prior_dev, float* value256_dev, cudaStream_t st) {
+int net_forward_legal_async(kb_net* net, NetWs& ws, const void* planes, int batch, const void* act_base, const void* nact_base, size_t stride,
+                            float* prior_dev, float* value256_dev, cudaStream_t st, int item0) {
     LegalRef lr;
     lr.act = reinterpret_cast<const uint8_t*>(act_base);
     lr.nact = reinterpret_cast<const uint8_t*>(nact_base);
     lr.stride = stride;
     lr.prior = prior_dev;
-    return net_forward_impl(net, planes, batch, nullptr, value256_dev, lr, st);
+    return net_forward_impl(net, ws, planes, batch, nullptr, value256_dev, lr, st, item0);
 }
 
 }  // namespace kb
@@ -1676,21 +1733,30 @@ int kb_net_create(kb_net** out, int filters, int residuals) {
     if (!n) return KB_ERR_ARG;
     n->filters = filters;
     n->residuals = residuals;
+    n->device = current_device();
     *out = n;
     return KB_OK;
 }
 
+static void ctx_free(InferCtx* c) {
+    ws_free(c->ws);
+    cudaFree(c->obs_dev); cudaFree(c->pol_dev); cudaFree(c->val_dev);
+    cudaFreeHost(c->obs_pin); cudaFreeHost(c->pol_pin); cudaFreeHost(c->val_pin);
+    if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+    if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    delete c;
+}
+
 int kb_net_destroy(kb_net* n) {
     if (!n) return KB_OK;
-    cudaStreamSynchronize(main_stream());
+    if (bind_device(n->device) == KB_OK) cudaDeviceSynchronize();
     for (auto& L : n->layers) {
         cudaFree(L.w);
         cudaFree(L.bias);
     }
     cudaFree(n->wv); cudaFree(n->fct); cudaFree(n->fcb);
-    cudaFree(n->P); cudaFree(n->X); cudaFree(n->Y); cudaFree(n->H);
-    cudaFree(n->nan_flag); cudaFree(n->obs_dev); cudaFree(n->pol_dev); cudaFree(n->val_dev);
-    cudaFree(n->fused_w); cudaFree(n->fused_bias); cudaFree(n->ts_dev); cudaFree(n->logits_dev);
+    for (InferCtx* c : n->ctx_free) ctx_free(c);
+    cudaFree(n->fused_w); cudaFree(n->fused_bias); cudaFree(n->ts_dev);
     delete n;
     return KB_OK;
 }
@@ -1712,12 +1778,21 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         set_error("weight blob has %zu floats, expected %zu for filters=%d residuals=%d", n_floats, kb_net_blob_floats(F, R), F, R);
         return KB_ERR_ARG;
     }
-    cudaStreamSynchronize(main_stream());
+    {
+        int rb = bind_device(net->device);
+        if (rb) return rb;
+    }
+    // NN::read / NN::train replace the weights under the exclusive lock (nn.cpp:206, 226): every call that reads them
+    // holds the lock shared until its kernels have completed, so nothing is in flight once the lock is ours; the device
+    // synchronisation covers callers of the asynchronous kb_net_forward_dev.
+    std::unique_lock<WeightLock> wlock(net->mu);
+    cudaDeviceSynchronize();
     for (auto& L : net->layers) {
         cudaFree(L.w);
         cudaFree(L.bias);
     }
     net->layers.clear();
+    net->loaded = false;
     BlobCursor c{blob, n_floats};
     std::vector<float> sc, sh;
     const int ntile = F == 64 ? 64 : 128;
@@ -1842,62 +1917,158 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
 
 size_t kb_net_planes_bytes(int batch) { return act_bytes(batch, IN_SLABS); }
 
+// Asynchronous, device-resident: the caller keeps planes / outputs in HBM.  The activation workspace is a per-thread
+// context of the net (returned to the free list right away: the next forward of the same thread on the same stream is
+// ordered behind this one).  The caller must not load new weights while forwards it has not waited for are in flight.
+static InferCtx* ctx_take(kb_net* net) {
+    std::lock_guard<std::mutex> g(net->ctx_mu);
+    if (!net->ctx_free.empty()) {
+        InferCtx* c = net->ctx_free.back();
+        net->ctx_free.pop_back();
+        return c;
+    }
+    return new (std::nothrow) InferCtx();
+}
+static void ctx_give(kb_net* net, InferCtx* c) {
+    std::lock_guard<std::mutex> g(net->ctx_mu);
+    net->ctx_free.push_back(c);
+}
+static thread_local InferCtx* tl_dev_ctx = nullptr;  // kb_net_forward_dev: one workspace per host thread, kept
+static thread_local kb_net* tl_dev_ctx_net = nullptr;
+
 int kb_net_forward_dev(kb_net* net, const void* planes_dev, int batch, float* policy_dev, float* value256_dev) {
     KB_REQUIRE_INIT();
     KB_ARG(net && planes_dev && policy_dev && value256_dev && batch > 0, "net/planes/policy/value/batch");
-    return net_forward_async(net, planes_dev, batch, policy_dev, value256_dev, main_stream());
+    int r = bind_device(net->device);
+    if (r) return r;
+    NetReadGuard lock(net);
+    if (tl_dev_ctx_net != net || !tl_dev_ctx) {
+        tl_dev_ctx = ctx_take(net);  // (kept by this thread for the life of the net: device-resident benches call this in loops)
+        tl_dev_ctx_net = net;
+        if (!tl_dev_ctx) return KB_ERR_ARG;
+    }
+    if ((r = ws_reserve(tl_dev_ctx->ws, net, batch, main_stream()))) return r;
+    return net_forward_async(net, tl_dev_ctx->ws, planes_dev, batch, policy_dev, value256_dev, main_stream());
 }
 
-static int net_stage(kb_net* net, int batch) {
-    if (batch <= net->stage_cap) return KB_OK;
-    cudaStreamSynchronize(main_stream());
-    cudaFree(net->obs_dev); cudaFree(net->pol_dev); cudaFree(net->val_dev);
-    KB_CUDA(cudaMalloc(&net->obs_dev, sizeof(float) * KB_OBSIZE * (size_t)batch));
-    KB_CUDA(cudaMalloc(&net->pol_dev, sizeof(float) * KB_PSIZE * (size_t)batch));
-    KB_CUDA(cudaMalloc(&net->val_dev, sizeof(float) * KB_VALUE_WIDTH * (size_t)batch));
-    net->stage_cap = batch;
+static int ctx_stage(InferCtx* c, int batch, cudaStream_t st) {
+    if (batch <= c->stage_cap) return KB_OK;
+    cudaStreamSynchronize(st);
+    cudaFree(c->obs_dev); cudaFree(c->pol_dev); cudaFree(c->val_dev);
+    cudaFreeHost(c->obs_pin); cudaFreeHost(c->pol_pin); cudaFreeHost(c->val_pin);
+    c->obs_dev = c->pol_dev = c->val_dev = c->obs_pin = c->pol_pin = c->val_pin = nullptr;
+    c->stage_cap = 0;
+    KB_CUDA(cudaMalloc(&c->obs_dev, sizeof(float) * KB_OBSIZE * (size_t)batch));
+    KB_CUDA(cudaMalloc(&c->pol_dev, sizeof(float) * KB_PSIZE * (size_t)batch));
+    KB_CUDA(cudaMalloc(&c->val_dev, sizeof(float) * KB_VALUE_WIDTH * (size_t)batch));
+    KB_CUDA(cudaMallocHost(&c->obs_pin, sizeof(float) * KB_OBSIZE * (size_t)batch));
+    KB_CUDA(cudaMallocHost(&c->pol_pin, sizeof(float) * KB_PSIZE * (size_t)batch));
+    KB_CUDA(cudaMallocHost(&c->val_pin, sizeof(float) * KB_VALUE_WIDTH * (size_t)batch));
+    if (!c->ev[0]) {
+        KB_CUDA(cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming));
+        KB_CUDA(cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming));
+    }
+    c->stage_cap = batch;
     return KB_OK;
 }
 
-int kb_net_forward_full(kb_net* net, const float* obs, int batch, float* policy, float* value256) {
+// true when the CUDA runtime can DMA straight from / into `p` (cudaMallocHost / cudaHostRegister memory)
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Host buffers in, host buffers out: observations [batch][1920] -> policy [batch][4672] (optional), value rows
+// ([batch][256] when value256, else the first `batch` floats of that tensor = NN::infer's value[i] = vh.flat[i], Q1).
+// Pinned caller buffers are used directly; pageable ones are staged through this call's private pinned buffers in
+// pieces, so the CPU copy of one piece overlaps the DMA of the previous one.  Everything -- workspace, staging, stream
+// (the calling thread's) -- is private to the call: any number of host threads may be inside at once (nn.cpp:164-168).
+static int net_infer_host(kb_net* net, const float* obs, int batch, float* policy, float* value, bool value256, bool keep_dbg) {
     KB_REQUIRE_INIT();
     KB_ARG(net && obs && batch > 0, "net/obs/batch");
-    int r;
-    if ((r = net_stage(net, batch)) || (r = net_reserve(net, batch))) return r;
+    int r = bind_device(net->device);
+    if (r) return r;
+    NetReadGuard lock(net);
+    InferCtx* c = ctx_take(net);
+    if (!c) return KB_ERR_ARG;
+    struct Give {
+        kb_net* n;
+        InferCtx* c;
+        ~Give() { ctx_give(n, c); }
+    } give{net, c};
     cudaStream_t st = main_stream();
-    KB_CUDA(cudaMemcpyAsync(net->obs_dev, obs, sizeof(float) * KB_OBSIZE * (size_t)batch, cudaMemcpyHostToDevice, st));
-    if ((r = obs_to_tall_launch(net->obs_dev, batch, net->P, st))) return r;
-    if ((r = net_forward_async(net, net->P, batch, net->pol_dev, net->val_dev, st))) return r;
-    if (policy) KB_CUDA(cudaMemcpyAsync(policy, net->pol_dev, sizeof(float) * KB_PSIZE * (size_t)batch, cudaMemcpyDeviceToHost, st));
-    if (value256) KB_CUDA(cudaMemcpyAsync(value256, net->val_dev, sizeof(float) * KB_VALUE_WIDTH * (size_t)batch, cudaMemcpyDeviceToHost, st));
+    if ((r = ctx_stage(c, batch, st)) || (r = ws_reserve(c->ws, net, batch, st))) return r;
+    const size_t obs_b = sizeof(float) * KB_OBSIZE * (size_t)batch, pol_b = sizeof(float) * KB_PSIZE * (size_t)batch;
+    const size_t val_b = sizeof(float) * (value256 ? KB_VALUE_WIDTH * (size_t)batch : (size_t)batch);
+    constexpr size_t PIECE = 1 << 20;
+    if (host_is_pinned(obs)) {
+        KB_CUDA(cudaMemcpyAsync(c->obs_dev, obs, obs_b, cudaMemcpyHostToDevice, st));
+    } else {
+        for (size_t off = 0; off < obs_b; off += PIECE) {
+            const size_t nb = obs_b - off < PIECE ? obs_b - off : PIECE;
+            memcpy((char*)c->obs_pin + off, (const char*)obs + off, nb);
+            KB_CUDA(cudaMemcpyAsync((char*)c->obs_dev + off, (char*)c->obs_pin + off, nb, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if ((r = obs_to_tall_launch(c->obs_dev, batch, c->ws.P, st))) return r;
+    if ((r = net_forward_async(net, c->ws, c->ws.P, batch, c->pol_dev, c->val_dev, st))) return r;
     int flag = 0;
-    KB_CUDA(cudaMemcpyAsync(&flag, net->nan_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    const bool pol_direct = policy && host_is_pinned(policy), val_direct = value && host_is_pinned(value);
+    if (value) KB_CUDA(cudaMemcpyAsync(val_direct ? value : c->val_pin, c->val_dev, val_b, cudaMemcpyDeviceToHost, st));
+    if (policy && pol_direct) KB_CUDA(cudaMemcpyAsync(policy, c->pol_dev, pol_b, cudaMemcpyDeviceToHost, st));
+    if (policy && !pol_direct) {
+        // D2H in pieces on the stream; the CPU copies piece i out of the pinned buffer while piece i + 1 is still arriving
+        size_t done = 0;
+        for (size_t off = 0; off < pol_b; off += PIECE) {
+            const size_t nb = pol_b - off < PIECE ? pol_b - off : PIECE;
+            KB_CUDA(cudaMemcpyAsync((char*)c->pol_pin + off, (char*)c->pol_dev + off, nb, cudaMemcpyDeviceToHost, st));
+            KB_CUDA(cudaEventRecord(c->ev[(off / PIECE) & 1], st));
+            if (off >= PIECE) {
+                KB_CUDA(cudaEventSynchronize(c->ev[((off / PIECE) - 1) & 1]));
+                memcpy((char*)policy + done, (char*)c->pol_pin + done, PIECE);
+                done += PIECE;
+            }
+        }
+        KB_CUDA(cudaStreamSynchronize(st));
+        memcpy((char*)policy + done, (char*)c->pol_pin + done, pol_b - done);
+    }
+    KB_CUDA(cudaMemcpyAsync(&flag, c->ws.nan_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     KB_CUDA(cudaStreamSynchronize(st));
+    if (value && !val_direct) memcpy(value, c->val_pin, val_b);
+    if (keep_dbg) net->dbg_ctx = c;
     if (flag) {
-        int zero = 0;
-        cudaMemcpy(net->nan_flag, &zero, sizeof(int), cudaMemcpyHostToDevice);
+        KB_CUDA(cudaMemsetAsync(c->ws.nan_flag, 0, sizeof(int), st));
+        KB_CUDA(cudaStreamSynchronize(st));
         set_error("inference output contains NaN");
         return KB_ERR_NAN;
     }
     return KB_OK;
 }
 
+int kb_net_forward_full(kb_net* net, const float* obs, int batch, float* policy, float* value256) {
+    return net_infer_host(net, obs, batch, policy, value256, true, true);
+}
+
 // NN::infer (nn.cpp:155-187).  The reference copies the first `batch` floats of its [batch,256]
 // value tensor, i.e. value[i] = vh[i / 256][i % 256]; reproduced bit for bit.
 int kb_net_infer(kb_net* net, const float* obs, int batch, float* policy, float* value) {
     KB_ARG(value && policy, "policy/value");
-    int r = kb_net_forward_full(net, obs, batch, policy, nullptr);
-    if (r) return r;
-    KB_CUDA(cudaMemcpy(value, net->val_dev, sizeof(float) * (size_t)batch, cudaMemcpyDeviceToHost));
-    return KB_OK;
+    return net_infer_host(net, obs, batch, policy, value, false, false);
 }
 
 // Test hook: download one board of an internal activation tensor as fp32 [channels][64].
 // which: 0 input planes (32 ch), 1 tower output X, 2 residual scratch Y, 3 policy hidden H (128 ch).
 int kb_net_debug_activation(kb_net* net, int which, int board, float* out, int* channels) {
     KB_REQUIRE_INIT();
-    KB_ARG(net && out && channels && board >= 0 && board < net->cap_boards, "net/out/board");
-    const uint4* buf = which == 0 ? net->P : which == 1 ? net->X : which == 2 ? net->Y : net->H;
+    KB_ARG(net && out && channels && board >= 0, "net/out/board");
+    KB_ARG(net->dbg_ctx && board < net->dbg_ctx->ws.cap_boards, "no kb_net_forward_full before this call / board out of range");
+    KB_ARG(which == 0 || net->dbg_ctx->ws.slabs > 0, "the fused tower keeps X / Y / H in shared memory (only which = 0 exists)");
+    const NetWs& ws = net->dbg_ctx->ws;
+    const uint4* buf = which == 0 ? ws.P : which == 1 ? ws.X : which == 2 ? ws.Y : ws.H;
     const int slabs = which == 0 ? IN_SLABS : which == 3 ? 2 : (net->filters + 63) / 64;
     const int chunks = slabs * 8;
     KB_CUDA(cudaStreamSynchronize(main_stream()));

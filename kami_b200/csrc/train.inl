@@ -816,6 +816,8 @@ struct TConv {            // one convolution of the network and everything the s
 }  // namespace
 
 struct kb_trainer {
+    int device = 0;
+    cudaStream_t last_stream = nullptr;
     int F = 0, R = 0, cap = 0, batch = 0;
     size_t n_floats = 0;
     float *params = nullptr, *grads = nullptr;
@@ -930,10 +932,10 @@ dim3 bn_grid(int slabs, int boards) {
 }
 
 int t_wgrad(kb_trainer* t, const TConv& c, const uint4* dy, const uint4* x, int x_slabs, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[16] = {};  // function attributes are per device
+    if (!configured[current_device() & 15]) {
         KB_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-        configured = true;
+        configured[current_device() & 15] = true;
     }
     WgradParams p;
     p.dy = reinterpret_cast<const uint8_t*>(dy);
@@ -952,10 +954,10 @@ int t_wgrad(kb_trainer* t, const TConv& c, const uint4* dy, const uint4* x, int 
         use_row = (e && e[0] == '1') ? 0 : 1;
     }
     if (p.ntaps == 9 && use_row) {  // one kernel row (three taps) x 128 co x 128 ci per CTA
-        static bool configured_row = false;
-        if (!configured_row) {
+        static bool configured_row[16] = {};
+        if (!configured_row[current_device() & 15]) {
             KB_CUDA(cudaFuncSetAttribute(k_wgrad_row, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM));
-            configured_row = true;
+            configured_row[current_device() & 15] = true;
         }
         const int kinds = 3 * ((p.co_slabs + 1) / 2) * ((p.ci_slabs + 1) / 2);
         int subsets = sm_count() / kinds;
@@ -1092,6 +1094,8 @@ int kb_trainer_create(kb_trainer** out, int filters, int residuals, int max_batc
            "out / filters in {64, 128, 256} / residuals / max_batch");
     kb_trainer* t = new (std::nothrow) kb_trainer();
     if (!t) return KB_ERR_ARG;
+    t->device = current_device();
+    t->last_stream = main_stream();
     t->F = filters;
     t->R = residuals;
     t->cap = max_batch;
@@ -1225,6 +1229,7 @@ int kb_trainer_create(kb_trainer** out, int filters, int residuals, int max_batc
 
 int kb_trainer_destroy(kb_trainer* t) {
     if (!t) return KB_OK;
+    KB_BIND(t);
     cudaStreamSynchronize(main_stream());
     for (void* p : t->allocs) cudaFree(p);
     delete t;
@@ -1235,6 +1240,7 @@ int kb_trainer_destroy(kb_trainer* t) {
 int kb_trainer_load_blob(kb_trainer* t, const float* blob, size_t n_floats) {
     KB_REQUIRE_INIT();
     KB_ARG(t && blob && n_floats == t->n_floats, "trainer / blob / size");
+    KB_BIND(t);
     KB_CUDA(cudaMemcpyAsync(t->params, blob, sizeof(float) * n_floats, cudaMemcpyHostToDevice, main_stream()));
     int r = t_repack(t, main_stream());
     if (r) return r;
@@ -1243,12 +1249,14 @@ int kb_trainer_load_blob(kb_trainer* t, const float* blob, size_t n_floats) {
 }
 int kb_trainer_export_blob(kb_trainer* t, float* blob, size_t n_floats) {
     KB_ARG(t && blob && n_floats == t->n_floats, "trainer / blob / size");
+    KB_BIND(t);
     KB_CUDA(cudaStreamSynchronize(main_stream()));
     KB_CUDA(cudaMemcpy(blob, t->params, sizeof(float) * n_floats, cudaMemcpyDeviceToHost));
     return KB_OK;
 }
 int kb_trainer_export_grads(kb_trainer* t, float* out, size_t n_floats) {
     KB_ARG(t && out && n_floats == t->n_floats, "trainer / out / size");
+    KB_BIND(t);
     KB_CUDA(cudaStreamSynchronize(main_stream()));
     KB_CUDA(cudaMemcpy(out, t->grads, sizeof(float) * n_floats, cudaMemcpyDeviceToHost));
     return KB_OK;
@@ -1257,6 +1265,7 @@ int kb_trainer_export_grads(kb_trainer* t, float* out, size_t n_floats) {
 // kb_trainer_forward_backward and kb_trainer_apply_sgd
 int kb_trainer_grad_buffer(kb_trainer* t, void** dev_ptr, size_t* n_floats) {
     KB_ARG(t && dev_ptr && n_floats, "trainer / out");
+    KB_BIND(t);
     *dev_ptr = t->grads;
     *n_floats = t->n_floats;
     return KB_OK;
@@ -1266,6 +1275,7 @@ int kb_trainer_grad_buffer(kb_trainer* t, void** dev_ptr, size_t* n_floats) {
 int kb_trainer_forward_backward(kb_trainer* t, const float* obs, const float* obs_p, const float* obs_v, int batch, float* loss) {
     KB_REQUIRE_INIT();
     KB_ARG(t && obs && obs_p && obs_v && batch >= 1 && batch <= t->cap, "trainer / arrays / 1 <= batch <= max_batch");
+    KB_BIND(t);
     cudaStream_t st = main_stream();
     KB_CUDA(cudaMemcpyAsync(t->obs_dev, obs, sizeof(float) * KB_OBSIZE * (size_t)batch, cudaMemcpyHostToDevice, st));
     KB_CUDA(cudaMemcpyAsync(t->pi_dev, obs_p, sizeof(float) * KB_PSIZE * (size_t)batch, cudaMemcpyHostToDevice, st));
@@ -1280,6 +1290,7 @@ int kb_trainer_forward_backward(kb_trainer* t, const float* obs, const float* ob
 int kb_trainer_forward_backward_dev(kb_trainer* t, const float* obs_dev, const float* obs_p_dev, const float* obs_v_dev, int batch, float* loss) {
     KB_REQUIRE_INIT();
     KB_ARG(t && obs_dev && obs_p_dev && obs_v_dev && batch >= 1 && batch <= t->cap, "trainer / arrays / 1 <= batch <= max_batch");
+    KB_BIND(t);
     int r = t_forward_backward(t, obs_dev, obs_p_dev, obs_v_dev, batch, main_stream());
     if (r) return r;
     if (loss) {
@@ -1292,6 +1303,7 @@ int kb_trainer_forward_backward_dev(kb_trainer* t, const float* obs_dev, const f
 // (after BatchNorm/ReLU/skip), for conv `layer` in [0, 2 + 2R) (conv1, residual convs, policyconv).
 int kb_trainer_debug_activation(kb_trainer* t, int layer, int which, int board, float* out, int* channels) {
     KB_ARG(t && out && channels && layer >= 0 && layer < (int)t->conv.size() - 1 && board >= 0 && board < t->batch, "trainer / layer / board");
+    KB_BIND(t);
     const TConv& c = t->conv[layer];
     const uint4* buf = which == 0 ? c.pre : c.post;
     KB_CUDA(cudaStreamSynchronize(main_stream()));
@@ -1316,6 +1328,7 @@ int kb_trainer_debug_activation(kb_trainer* t, int layer, int which, int board, 
 int kb_trainer_apply_sgd(kb_trainer* t, float lr, float grad_scale) {
     KB_REQUIRE_INIT();
     KB_ARG(t, "trainer");
+    KB_BIND(t);
     cudaStream_t st = main_stream();
     k_sgd<<<1024, 256, 0, st>>>(t->params, t->grads, t->n_floats, lr * grad_scale);
     KB_CUDA(cudaGetLastError());
