@@ -36,7 +36,8 @@ FILTERS, RESIDUALS = 64, 2          # options.def.yml:29,53
 SELFPLAY_NODES = 1024               # options.def.yml selfplay_nodes
 NODE_CAPACITY = 1 << 19  # 2 x 10 MB per tree: the copying collector runs about once per 40 moves
 TOWER64_DRAM_BYTES_PER_LAUNCH = 12861440  # profiles/r01_ncu_summary_v3.txt
-PREROLL_STEPS = 1536                # untimed: grows the synthetic trees to steady state (first moves made)
+PREROLL_STEPS = 4096                # untimed: grows the synthetic games to steady state (every tree has moved a few times and
+                                    # the trees' budgets are out of phase, so moves are spread evenly over the steps)
 METRIC = "selfplay_nn_evals_per_sec"
 UNIT = "evals/s"
 
@@ -277,6 +278,8 @@ def workload_config():
                         "(2x64 tower, 1024-node budget/move, cpuct 1.5, bootstrap 20%, noise 0.05), random-init weights",
             "trees_per_gpu": TREES_PER_GPU, "filters": FILTERS, "residuals": RESIDUALS, "selfplay_nodes": SELFPLAY_NODES,
             "evals_per_step_per_gpu": TREES_PER_GPU,
+            "reference_arm": "--impl reference runs the reference's stock CPU shape of this workload: 3 inference threads x 16 "
+                             "trees (options.def.yml inference_threads / selfplay_batch) sharing one LibTorch-CPU network, from fresh trees",
             "l2": "inputs larger than L2: live node pools ~0.6 MB x 1024 trees per GPU >> 126 MB, no flush"}
 
 
@@ -435,7 +438,9 @@ def encoder_leg(api, L, pool, hbm_peak, peak_kind, n=131072, reps=10):
 def infer256_leg(api, L, pool, net, reps=20):
     """BASELINE config 2 (the reference's test/nncuda.cpp / test/nn.cpp loop at batch 256): 256 synthetic positions ->
     planes -> NN::infer through the host-buffer call (H2D observations, D2H policy [256][4672] + value inside the timed
-    region), next to the unmodified reference NN::infer (LibTorch CPU fp32, all host threads) on the same input."""
+    region).  Ours with pageable buffers (what an unmodified caller passes) and with pinned ones (kb_host_register),
+    next to the UNMODIFIED reference NN::infer on the same input: its own CUDA path (LibTorch CUDA on this GPU,
+    test/nncuda.cpp's configuration: fp32 weights, cuDNN with LibTorch's default TF32 convolutions) and its CPU path."""
     pos = pool.leaf_positions()[:256]
     obs = api.encode_planes(pos)
     out = {"batch": 256, "filters": FILTERS, "residuals": RESIDUALS}
@@ -445,8 +450,41 @@ def infer256_leg(api, L, pool, net, reps=20):
         pol, val = net.infer(obs)
     dt = (time.time() - t0) / reps
     out["ours"] = {"ms_per_call": dt * 1e3, "pred_per_sec": 256 / dt, "api": "kb_net_infer, pageable host buffers"}
-    import harness as H  # CPU baseline part only: the compiled reference under oracle/_ref
+    pobs, ppol, pval = obs.copy(), np.zeros((256, 4672), np.float32), np.zeros(256, np.float32)
+    for a in (pobs, ppol, pval):
+        api._ck(L.kb_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes))
+    try:
+        f = lambda: api._ck(L.kb_net_infer(net.h, api._fp(pobs), 256, api._fp(ppol), api._fp(pval)))
+        f()
+        t0 = time.time()
+        for _ in range(reps):
+            f()
+        dp = (time.time() - t0) / reps
+        out["ours_pinned"] = {"ms_per_call": dp * 1e3, "pred_per_sec": 256 / dp, "api": "kb_net_infer, caller buffers pinned with kb_host_register",
+                              "same_bits_as_pageable": bool(np.array_equal(ppol, pol) and np.array_equal(pval, val))}
+    finally:
+        for a in (pobs, ppol, pval):
+            L.kb_host_unregister(a.ctypes.data_as(C.c_void_p))
+    import harness as H  # baselines only: the compiled reference under oracle/_ref
 
+    try:
+        LC = H.ref_nn_cuda_lib()
+        if LC is not None:
+            rn = H.RefNN(FILTERS, RESIDUALS, seed=1, force_cpu=False, lib=LC)
+            if rn.is_cuda():
+                for _ in range(5):
+                    rn.infer(obs)
+                t0 = time.time()
+                for _ in range(reps):
+                    rn.infer(obs)
+                dc = (time.time() - t0) / reps
+                out["reference_cuda"] = {"ms_per_call": dc * 1e3, "pred_per_sec": 256 / dc,
+                                         "what": "unmodified kami::NN::infer on LibTorch CUDA (cuDNN, fp32/TF32), same GPU, pageable host buffers"}
+            else:
+                out["reference_cuda"] = {"unavailable": "torch::cuda::is_available() is false in the reference build"}
+            del rn
+    except Exception as e:
+        out["reference_cuda"] = {"error": str(e)[:200]}
     if H.ref_nn_lib() is not None:
         nn = H.RefNN(FILTERS, RESIDUALS, seed=1, force_cpu=True)
         H.ref_nn_lib().ref_nn_set_threads(max(1, os.cpu_count() or 1))
@@ -457,6 +495,48 @@ def infer256_leg(api, L, pool, net, reps=20):
         dr = (time.time() - t0) / 3
         out["reference_cpu"] = {"ms_per_call": dr * 1e3, "pred_per_sec": 256 / dr, "cores": os.cpu_count() or 1}
     return out
+
+
+def selfplay_20x256_leg(api, L, dist, local, rank, kw, per_rank_seed, steps=24):
+    """SURVEY 8(d) configs 3-4 "F=64,R=2 AND F=256,R=20": the same 1024-tree self-play step with BASELINE config 5's
+    network (per-layer tcgen05 convs, legal-move softmax), resident."""
+    import kami_b200
+
+    big = kami_b200.NN(256, 20)
+    big.load_blob(random_blob(256, 20, seed=1))
+    pool = kami_b200.TreePool(TREES_PER_GPU, 1 << 17, api.tree_cfg(seed=per_rank_seed(7000, rank), **kw))
+    pool.step(big, 6)
+    pool.reset_stats()
+    ms = C.c_float()
+    barrier(dist, local)
+    L.kb_dev_sync()
+    L.kb_timer_start()
+    pool.step(big, steps)
+    L.kb_timer_stop(C.byref(ms))
+    barrier(dist, local)
+    t = reduce_max(dist, local, ms.value)
+    ev = reduce_sum(dist, local, float(pool.stats()["evals"]))
+    t_f, h_f = big.flops()
+    hbm, tfp, tfs, kind = peaks()
+    world = dist.get_world_size() if dist is not None else 1
+    v = ev / (t * 1e-3)
+    return {"filters": 256, "residuals": 20, "trees_per_gpu": TREES_PER_GPU, "steps": steps, "ms_per_step": t / steps, "evals_per_sec": v,
+            "n_gpus": world, "tflops_per_gpu": v / world * (t_f + h_f) / 1e12, "frac_of_bf16_peak_per_gpu": v / world * (t_f + h_f) / 1e12 / tfp,
+            "peak_kind": kind, "note": "trees a few moves old (6 warm-up steps): the step is the network"}
+
+
+def selfplay_cpp_leg(devices, seconds=5.0):
+    """The e2e the C++ product serves: kami::Selfplay (kami/selfplay.h) start()/stop() from kami/tests/selfplay_e2e.cpp --
+    inference threads on device pools, finished games drained into the host ReplayBuffer; one host process, one
+    inference thread per GPU."""
+    exe = os.path.join(ROOT, "kami", "_dropin", "selfplay_e2e")
+    if not os.path.exists(exe):
+        return {"unavailable": "kami/_dropin/selfplay_e2e not built"}
+    out = subprocess.run([exe, str(seconds), str(devices)], capture_output=True, timeout=120)
+    for line in out.stdout.decode().splitlines():
+        if line.startswith("{"):
+            return json.loads(line)
+    return {"error": (out.stderr.decode() or out.stdout.decode())[-300:]}
 
 
 def run_ours(args, rank, world, local, dist):
@@ -551,6 +631,29 @@ def run_ours(args, rank, world, local, dist):
 
     extras = {}
     cpu = None
+    # the same host-buffer loop with the compact forms on the wire (kb_pool_step_hostio_compact): 80-byte leaf positions
+    # instead of [1920] fp32 rows, [128] legal-move priors instead of [4672] policy rows
+    try:
+        from kami_b200 import api as _api
+
+        leaves_h = np.zeros(n, _api.POSITION_DTYPE)
+        prior_h = pinned((n, 128))
+        api._ck(L.kb_host_register(leaves_h.ctypes.data_as(C.c_void_p), leaves_h.nbytes))
+        try:
+            pool.step_hostio_compact(net, 3, leaves_h, prior_h, val_h)
+            pool.reset_stats()
+            ck = max(3, min(args.steps, 1000))
+            ms_c = timed_steps(lambda k: pool.step_hostio_compact(net, k, leaves_h, prior_h, val_h), ck)
+            ev_c = reduce_sum(dist, local, float(pool.stats()["evals"]))
+        finally:
+            L.kb_host_unregister(leaves_h.ctypes.data_as(C.c_void_p))
+        if rank == 0:
+            extras["e2e_compact"] = {"value": ev_c / (ms_c * 1e-3), "unit": UNIT, "steps": ck, "ms_per_step": ms_c / ck,
+                                     "h2d_bytes_per_step": n * (80 + 512 + 4), "d2h_bytes_per_step": n * (80 + 512 + 4),
+                                     "api": "kb_pool_step_hostio_compact: leaf positions D2H -> H2D -> encode -> tower -> legal priors + value D2H -> H2D -> expand"}
+    except Exception as e:
+        if rank == 0:
+            extras["e2e_compact"] = {"error": str(e)[:200]}
     if rank == 0 and not args.no_extras:
         # 20x256 tower (BASELINE config 5's network) forward only: % of dense BF16 peak at batch 1024
         try:
@@ -605,6 +708,14 @@ def run_ours(args, rank, world, local, dist):
         except Exception as e:
             if rank == 0:
                 extras["train_20x256"] = {"error": str(e)}
+    if not args.no_extras:
+        try:
+            sp = selfplay_20x256_leg(api, L, dist, local, rank, kw, per_rank_seed)
+            if rank == 0:
+                extras["selfplay_20x256"] = sp
+        except Exception as e:
+            if rank == 0:
+                extras["selfplay_20x256"] = {"error": str(e)[:200]}
     if not args.no_extras and world > 1 and 8192 % world == 0:
         # BASELINE config 4 exactly: 8192 concurrent games in total, sharded by game over the N GPUs (8192 / N trees per
         # GPU, no collective), same network and budget.  The headline line above keeps 1024 trees per GPU (weak scaling).
@@ -625,6 +736,16 @@ def run_ours(args, rank, world, local, dist):
                 extras["config4_8192_games"] = {"error": str(e)}
     for p in bufs:
         L.kb_host_free_pinned(p)
+    del pool
+    if not args.no_extras:
+        # one C++ host process driving all N GPUs through kami::Selfplay (the other ranks idle at the barrier)
+        barrier(dist, local)
+        if rank == 0:
+            try:
+                extras["e2e_selfplay_cpp"] = selfplay_cpp_leg(world)
+            except Exception as e:
+                extras["e2e_selfplay_cpp"] = {"error": str(e)[:200]}
+        barrier(dist, local)
     if rank != 0:
         return
     out = {

@@ -55,7 +55,9 @@ class WriterFirstSharedMutex {
 
 class NN {
    private:
-    kb_net* net = nullptr;
+    kb_net* net = nullptr;                    // the primary replica (device `device0`)
+    int device0 = 0;
+    std::vector<std::pair<int, kb_net*>> replicas;  // weight replicas on other GPUs of the box (one per GPU)
     int width, height, features, psize;
     int filters, residuals;
     WriterFirstSharedMutex mut;
@@ -110,6 +112,7 @@ class NN {
         filters = options::getInt("filters", 256);     // nn.cpp:42
         residuals = options::getInt("residuals", 2);   // nn.cpp:43
         check(kb_net_create(&net, filters, residuals));
+        device0 = kb_current_device();
         random_init(std::random_device{}());
         check(kb_net_load_blob(net, blob.data(), blob.size()));
     }
@@ -120,9 +123,13 @@ class NN {
         generation = other->generation;
         blob = other->blob;
         check(kb_net_create(&net, filters, residuals));
+        device0 = kb_current_device();
         check(kb_net_load_blob(net, blob.data(), blob.size()));
     }
-    ~NN() { kb_net_destroy(net); }
+    ~NN() {
+        kb_net_destroy(net);
+        for (auto& r : replicas) kb_net_destroy(r.second);
+    }
     NN(const NN&) = delete;
     NN& operator=(const NN&) = delete;
 
@@ -135,6 +142,33 @@ class NN {
     int obsize() const { return width * height * features; }
     int polsize() const { return psize; }
     kb_net* handle() { return net; }
+    // Self-play shards by game over the GPUs of the box with no collective: every GPU holds a full weight
+    // replica.  handle(d) creates the replica on device d on first use (the calling thread stays bound to d: that is
+    // what an inference thread serving GPU d wants); read() / train() / load_blob() refresh every replica.
+    kb_net* handle(int device) {
+        {
+            std::shared_lock<WriterFirstSharedMutex> g(mut);
+            if (device < 0 || device == device0) return net;
+            for (auto& r : replicas)
+                if (r.first == device) return r.second;
+        }
+        std::unique_lock<WriterFirstSharedMutex> g(mut);
+        for (auto& r : replicas)
+            if (r.first == device) return r.second;
+        check(kb_init(device));
+        kb_net* rep = nullptr;
+        check(kb_net_create(&rep, filters, residuals));
+        check(kb_net_load_blob(rep, blob.data(), blob.size()));
+        replicas.emplace_back(device, rep);
+        return rep;
+    }
+
+   private:
+    void refresh_replicas(const std::vector<float>& b) {  // caller holds `mut` exclusively
+        for (auto& r : replicas) check(kb_net_load_blob(r.second, b.data(), b.size()));
+    }
+
+   public:
 
     // nn.cpp:155-187: host buffers in and out, NaN -> runtime_error, value[i] = vh.flat[i]
     void infer(float* input, int batch, float* policy, float* value) {
@@ -146,9 +180,10 @@ class NN {
     // The device-resident form of the inference loop's NN::infer call (selfplay.cpp:196): `iters` rounds of
     // select -> tower -> expand on a pool, under the same shared lock NN::infer takes (nn.cpp:166), so read() / train()
     // never swap the weights under a running step.
-    void pool_step(kb_pool* pool, int iters) {
+    void pool_step(kb_pool* pool, int iters, int device = -1) {
+        kb_net* h = handle(device);
         std::shared_lock<WriterFirstSharedMutex> g(mut);
-        int rc = kb_pool_step(pool, net, iters);
+        int rc = kb_pool_step(pool, h, iters);
         if (rc == KB_ERR_NAN) throw std::runtime_error("inference policy output contains NaN");
         check(rc);
     }
@@ -211,6 +246,7 @@ class NN {
         std::vector<float> b(blob.size());
         check(kb_trainer_export_blob(tr, b.data(), b.size()));
         check(kb_net_load_blob(net, b.data(), b.size()));
+        refresh_replicas(b);
         blob.swap(b);
     }
     // Checkpoint = "KB20" + filters + residuals + generation + fp32 blob.  (The reference writes a
@@ -233,6 +269,7 @@ class NN {
         std::vector<float> b(kb_net_blob_floats(filters, residuals));
         if (!f.read((char*)b.data(), b.size() * sizeof(float))) throw std::runtime_error("truncated model " + path);
         check(kb_net_load_blob(net, b.data(), b.size()));
+        refresh_replicas(b);
         blob.swap(b);
         generation = hdr[3];
     }
@@ -241,6 +278,7 @@ class NN {
         std::unique_lock<WriterFirstSharedMutex> g(mut);
         check(kb_net_load_blob(net, data, n));
         blob.assign(data, data + n);
+        refresh_replicas(blob);
     }
 };
 }  // namespace kami

@@ -67,6 +67,10 @@ class Selfplay {
     };
     Status status;
     ReplayBuffer& get_rbuf() { return replay_buffer; }
+    // extension (not in the reference): totals over the inference threads, for throughput reporting
+    unsigned long long evals() const { return total_evals.load(); }
+    unsigned long long moves() const { return total_moves.load(); }
+    unsigned long long games() const { return total_games.load(); }
     // selfplay.h:73-80: the next game an inference thread finishes is written out as PGN movetext
     std::string get_next_pgn() {
         wants_pgn = true;
@@ -84,9 +88,17 @@ class Selfplay {
     std::string ret_pgn;
     std::mutex pgn_lock;
     std::list<std::atomic<int>> partial_trajectories;
+    std::atomic<unsigned long long> total_evals{0}, total_moves{0}, total_games{0};
 
     void inference_main(int id) {
         std::cout << "Starting inference thread: " << id << std::endl;
+        // Games never interact (selfplay.cpp:97): with b200_devices = N the inference threads are spread over the first N
+        // GPUs of the box (thread id -> GPU id mod N), each with its own weight replica, node pools and streams; no
+        // collective on this path.  0 = every visible GPU.
+        int ndev = options::getInt("b200_devices", 1);
+        if (ndev <= 0) ndev = kb_device_count();
+        const int dev = ndev > 1 ? id % ndev : -1;
+        if (dev >= 0) kb_check(kb_init(dev));
         kb_tree_cfg cfg;
         kb_check(kb_tree_default_cfg(&cfg));
         cfg.cpuct = options::getFloat("cpuct", 1.0f);
@@ -111,6 +123,7 @@ class Selfplay {
         const bool flush_old_trees = options::getInt("flush_old_trees", 1) != 0;  // selfplay.cpp:61
         int source_generation = model->get_generation();                          // selfplay.cpp:103
         long long flushed = 0;
+        kb_pool_stats seen = {};
         const int iters_per_call = options::getInt("b200_iters_per_call", 64);
         std::vector<int32_t> game_actions(4096);
         bool game_requested = false;
@@ -127,9 +140,13 @@ class Selfplay {
                 kb_check(kb_pool_flush_trees(pool));
                 source_generation = gen;
             }
-            model->pool_step(pool, iters_per_call);
+            model->pool_step(pool, iters_per_call, dev);
             kb_pool_stats st;
             kb_check(kb_pool_get_stats(pool, &st));
+            total_evals += st.evals - seen.evals;
+            total_moves += st.moves - seen.moves;
+            total_games += st.games - seen.games;
+            seen = st;
             *partial = (int)((long long)(st.moves - st.samples) - flushed);  // positions recorded in games still being played (selfplay.cpp:150-151)
             int m = 0;
             do {

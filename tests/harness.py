@@ -382,10 +382,27 @@ def uci(mv):
 _refnn = None
 
 
+def ref_nn_cuda_lib():
+    """The same reference NN shim with LibTorch's CUDA backend linked in (oracle/Makefile): the reference's own GPU path,
+    loaded only by bench.py's config-2 leg on the GPU box."""
+    global _refnn_cuda
+    if _refnn_cuda is None:
+        _refnn_cuda = _load_ref_nn(os.path.join(os.path.dirname(ref_nn_path()), "libkami_ref_nn_cuda.so"))
+    return _refnn_cuda
+
+
+_refnn_cuda = None
+
+
 def ref_nn_lib():
     global _refnn
     if _refnn is None:
-        p = ref_nn_path()
+        _refnn = _load_ref_nn(ref_nn_path())
+    return _refnn
+
+
+def _load_ref_nn(p):
+    if True:
         if not os.path.exists(p):
             return None
         L = C.CDLL(p)
@@ -405,15 +422,14 @@ def ref_nn_lib():
         L.ref_nn_read.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_nn_generation.argtypes = [C.c_void_p]
         L.ref_nn_train.argtypes = [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
-        _refnn = L
-    return _refnn
+        return L
 
 
 class RefNN:
     """The unmodified reference kami::NN (kami/nn/nn.cpp) on LibTorch."""
 
-    def __init__(self, filters, residuals, seed=1, force_cpu=True):
-        self.L = ref_nn_lib()
+    def __init__(self, filters, residuals, seed=1, force_cpu=True, lib=None):
+        self.L = lib or ref_nn_lib()
         self.filters, self.residuals = filters, residuals
         self.h = self.L.ref_nn_new(filters, residuals, seed, int(force_cpu))
         self.index = {}
