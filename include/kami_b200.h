@@ -216,6 +216,28 @@ int kb_pool_drain_samples(kb_pool* p, int max_samples, float* obs /*[m][1920]*/,
 int kb_pool_request_game(kb_pool* p);
 int kb_pool_take_game(kb_pool* p, int32_t* actions, int cap, int* count);
 
+/* ---- arena: kami::eval, kami/evaluate.h:6, kami/evaluate.cpp:10-160 --------------------------------------------
+ * `games` device-resident trees searched `nodes` deep; every leaf is evaluated by the network whose turn it is at the
+ * leaf (two batches of at most `batch` rows per round, bootstrap off), greedy moves.  One kb_arena_round is one pass of
+ * the reference's while-loop body (evaluate.cpp:45-151); the caller keeps the score and the early-stop rule
+ * (evaluate.cpp:100-126) by reading the finished games, which arrive in the reference's order.  colours[i] = the side
+ * the candidate plays in tree i (evaluate.cpp:18-22: (rand() % 2) * 2 - 1). */
+typedef struct kb_arena kb_arena;
+typedef struct kb_arena_game {
+    int32_t tree;    /* tree whose game ended */
+    float result;    /* terminal value, White's point of view (env.h:288-385) */
+    int32_t colour;  /* side the candidate played in that game: score += result * colour / 2 + 0.5 (evaluate.cpp:101) */
+} kb_arena_game;
+int kb_arena_create(kb_arena** out, int games, int batch, int nodes, const kb_tree_cfg* cfg, const int32_t* colours, int n_colours);
+int kb_arena_destroy(kb_arena* a);
+int kb_arena_round(kb_arena* a, kb_net* current, kb_net* candidate, kb_arena_game* finished, int cap, int* n_finished);
+/* the same round in two halves, for hosts that evaluate the leaves themselves: begin() hands out the two networks' input
+ * batches exactly as the reference passes them to NN::infer (host fp32 [n][1920]), end() takes policy [n][4672] / value [n] */
+int kb_arena_begin(kb_arena* a, kb_arena_game* finished, int cap, int* n_finished, float* cur_obs, int* cur_n, float* cd_obs, int* cd_n);
+int kb_arena_end(kb_arena* a, const float* cur_policy, const float* cur_value, const float* cd_policy, const float* cd_value);
+kb_pool* kb_arena_pool(kb_arena* a);                      /* the trees, for kb_tree_digest / kb_tree_n / ... */
+int kb_arena_colours(kb_arena* a, int32_t* out, int cap); /* current colour table */
+
 /* timing helper: elapsed ms of the last kb_pool_step / kb_net_forward_dev per phase */
 typedef struct kb_phase_ms {
     float select, encode, tower, heads, expand, total;

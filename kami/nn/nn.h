@@ -187,6 +187,14 @@ class NN {
         if (rc == KB_ERR_NAN) throw std::runtime_error("inference policy output contains NaN");
         check(rc);
     }
+    // One round of the device-resident arena (kb_arena_round) with this network as the candidate and `current` as the
+    // incumbent, both under their shared locks like the two NN::infer calls of evaluate.cpp:136-151.
+    int arena_round(kb_arena* arena, NN* current, kb_arena_game* finished, int cap, int* n) {
+        std::shared_lock<WriterFirstSharedMutex> g1(mut);
+        if (current == this) return kb_arena_round(arena, net, net, finished, cap, n);
+        std::shared_lock<WriterFirstSharedMutex> g2(current->mut);
+        return kb_arena_round(arena, current->net, net, finished, cap, n);
+    }
     // nn.cpp:224-377: `epochs` passes of shuffled mini-batches of `training_batchsize`, plain SGD with
     // lr = training_mlr / 1000, BatchNorm in training mode, ++generation, back to eval mode.  Each mini-batch
     // is one kb_trainer_forward_backward + kb_trainer_apply_sgd (tcgen05 forward / dgrad / wgrad).  Like the

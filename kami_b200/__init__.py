@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     NN,
     Trainer,
     TreePool,
+    Arena,
     TreeCfg,
     Position,
     lib,

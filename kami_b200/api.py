@@ -54,6 +54,10 @@ class PoolStats(C.Structure):
                                           "kernel_launches")]
 
 
+class ArenaGame(C.Structure):
+    _fields_ = [("tree", C.c_int32), ("result", C.c_float), ("colour", C.c_int32)]
+
+
 class PhaseMs(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("select", "encode", "tower", "heads", "expand", "total")]
 
@@ -143,6 +147,13 @@ _SIGS = {
     "kb_pool_leaf_positions": (C.c_int, [_P, _P]),
     "kb_pool_expand": (C.c_int, [_P, _f32p, _f32p, C.c_int]),
     "kb_pool_expand_dev": (C.c_int, [_P, _P, _P, C.c_int]),
+    "kb_arena_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.POINTER(TreeCfg), _i32p, C.c_int]),
+    "kb_arena_destroy": (C.c_int, [_P]),
+    "kb_arena_round": (C.c_int, [_P, _P, _P, C.POINTER(ArenaGame), C.c_int, _i32p]),
+    "kb_arena_begin": (C.c_int, [_P, C.POINTER(ArenaGame), C.c_int, _i32p, _f32p, _i32p, _f32p, _i32p]),
+    "kb_arena_end": (C.c_int, [_P, _f32p, _f32p, _f32p, _f32p]),
+    "kb_arena_pool": (_P, [_P]),
+    "kb_arena_colours": (C.c_int, [_P, _i32p, C.c_int]),
     "kb_pool_leaf_actions": (C.c_int, [_P, _i32p, _i32p]),
     "kb_pool_expand_compact": (C.c_int, [_P, _f32p, _f32p, C.c_int]),
     "kb_pool_step": (C.c_int, [_P, _P, C.c_int]),
@@ -588,6 +599,58 @@ class TreePool:
 
     def tree(self, i):
         return MCTS(pool=self, index=i)
+
+
+class Arena:
+    """Device-resident kami::eval (evaluate.cpp:10-160): `games` trees, two networks, one round per call."""
+
+    def __init__(self, games, batch, nodes, colours, cfg=None):
+        self.L = lib()
+        self.games, self.batch, self.nodes = games, batch, nodes
+        self.cfg = cfg or tree_cfg()
+        col = np.ascontiguousarray(colours, np.int32)
+        self.h = _P()
+        _ck(self.L.kb_arena_create(C.byref(self.h), games, batch, nodes, C.byref(self.cfg), _ip(col), len(col)))
+        self._ev = (ArenaGame * games)()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.kb_arena_destroy(self.h)
+            self.h = None
+
+    def _events(self, n):
+        return [(self._ev[i].tree, self._ev[i].result, self._ev[i].colour) for i in range(n)]
+
+    def round(self, current, candidate):
+        """-> [(tree, result, colour)] of the games that ended, in the reference's order."""
+        n = C.c_int32()
+        _ck(self.L.kb_arena_round(self.h, current.h, candidate.h, self._ev, self.games, C.byref(n)))
+        return self._events(n.value)
+
+    def begin(self):
+        """-> (finished games, current network's input rows, candidate's input rows)."""
+        n, cn, dn = C.c_int32(), C.c_int32(), C.c_int32()
+        cur = np.zeros((self.batch, OBSIZE), np.float32)
+        cd = np.zeros((self.batch, OBSIZE), np.float32)
+        _ck(self.L.kb_arena_begin(self.h, self._ev, self.games, C.byref(n), _fp(cur), C.byref(cn), _fp(cd), C.byref(dn)))
+        return self._events(n.value), cur[:cn.value], cd[:dn.value]
+
+    def end(self, cur_policy, cur_value, cd_policy, cd_value):
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (cur_policy, cur_value, cd_policy, cd_value)]
+        _ck(self.L.kb_arena_end(self.h, *[_fp(a) if a.size else None for a in arrs]))
+
+    def colours(self):
+        out = np.zeros(self.games, np.int32)
+        _ck(self.L.kb_arena_colours(self.h, _ip(out), self.games))
+        return out
+
+    def tree(self, i):
+        """Read-only view of tree i (digest / n / root_children)."""
+        view = TreePool.__new__(TreePool)
+        view.L, view.h, view.n, view.cfg = self.L, None, self.games, self.cfg
+        t = MCTS.__new__(MCTS)
+        t.pool, t.i, t.L, t.ph = view, i, self.L, _P(self.L.kb_arena_pool(self.h))
+        return t
 
 
 class MCTS:
