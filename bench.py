@@ -36,8 +36,14 @@ FILTERS, RESIDUALS = 64, 2          # options.def.yml:29,53
 SELFPLAY_NODES = 1024               # options.def.yml selfplay_nodes
 NODE_CAPACITY = 1 << 19  # 2 x 10 MB per tree: the copying collector runs about once per 40 moves
 TOWER64_DRAM_BYTES_PER_LAUNCH = 12861440  # profiles/r01_ncu_summary_v3.txt
-PREROLL_STEPS = 4096                # untimed: grows the synthetic games to steady state (every tree has moved a few times and
-                                    # the trees' budgets are out of phase, so moves are spread evenly over the steps)
+# State preparation (untimed).  The step gets slower as the synthetic games leave the opening (more legal moves per
+# position, terminal leaves to absorb: 84 us/step after 5 k steps from fresh trees, 118-135 us from 20 k steps on,
+# tools/steady_state.py), so the timed region must not start from young games.  The games are aged quickly with a small
+# node budget (a move every ~30 steps: each tree plays ~200 plies, i.e. the pool holds games in every phase), then the
+# trees are rebuilt under the full budget until every tree has moved a few times at 1024 nodes.
+AGE_STEPS, AGE_NODES = 6000, 32
+PREROLL_STEPS = 3500
+TERMINAL_CAP = 4                    # kb_pool_set_terminal_cap: see include/kami_b200.h
 METRIC = "selfplay_nn_evals_per_sec"
 UNIT = "evals/s"
 
@@ -278,6 +284,10 @@ def workload_config():
                         "(2x64 tower, 1024-node budget/move, cpuct 1.5, bootstrap 20%, noise 0.05), random-init weights",
             "trees_per_gpu": TREES_PER_GPU, "filters": FILTERS, "residuals": RESIDUALS, "selfplay_nodes": SELFPLAY_NODES,
             "evals_per_step_per_gpu": TREES_PER_GPU,
+            "state": "games aged to steady state before the timed region: %d steps at a %d-node budget, then %d steps at the full budget" % (
+                AGE_STEPS, AGE_NODES, PREROLL_STEPS),
+            "terminal_cap": "a tree that absorbed %d terminal visits in one step sits the step out (kb_pool_set_terminal_cap); value counts real "
+                            "evaluations only" % TERMINAL_CAP,
             "reference_arm": "--impl reference runs the reference's stock CPU shape of this workload: 3 inference threads x 16 "
                              "trees (options.def.yml inference_threads / selfplay_batch) sharing one LibTorch-CPU network, from fresh trees",
             "l2": "inputs larger than L2: live node pools ~0.6 MB x 1024 trees per GPU >> 126 MB, no flush"}
@@ -467,22 +477,15 @@ def infer256_leg(api, L, pool, net, reps=20):
             L.kb_host_unregister(a.ctypes.data_as(C.c_void_p))
     import harness as H  # baselines only: the compiled reference under oracle/_ref
 
-    try:
-        LC = H.ref_nn_cuda_lib()
-        if LC is not None:
-            rn = H.RefNN(FILTERS, RESIDUALS, seed=1, force_cpu=False, lib=LC)
-            if rn.is_cuda():
-                for _ in range(5):
-                    rn.infer(obs)
-                t0 = time.time()
-                for _ in range(reps):
-                    rn.infer(obs)
-                dc = (time.time() - t0) / reps
-                out["reference_cuda"] = {"ms_per_call": dc * 1e3, "pred_per_sec": 256 / dc,
-                                         "what": "unmodified kami::NN::infer on LibTorch CUDA (cuDNN, fp32/TF32), same GPU, pageable host buffers"}
-            else:
-                out["reference_cuda"] = {"unavailable": "torch::cuda::is_available() is false in the reference build"}
-            del rn
+    try:  # in a process of its own: LibTorch's CUDA backend stays out of this one
+        import tempfile
+
+        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
+            np.save(f, obs)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_cuda_infer.py"), f.name, str(reps)], capture_output=True, timeout=180)
+        os.unlink(f.name)
+        lines = [ln for ln in r.stdout.decode().splitlines() if ln.startswith("{")]
+        out["reference_cuda"] = json.loads(lines[-1]) if lines else {"error": "exit code %d: %s" % (r.returncode, r.stderr.decode()[-200:])}
     except Exception as e:
         out["reference_cuda"] = {"error": str(e)[:200]}
     if H.ref_nn_lib() is not None:
@@ -565,10 +568,16 @@ def run_ours(args, rank, world, local, dist):
         barrier(dist, local)
         return reduce_max(dist, local, ms.value)
 
-    # state preparation (untimed): grow the synthetic games to steady state, then W warm-up steps
+    # state preparation (untimed): age the synthetic games to steady state, then W warm-up steps
+    pool.set_terminal_cap(TERMINAL_CAP)
     if args.preroll > 0:
+        pool.set_selfplay_nodes(AGE_NODES)
+        pool.step(net, AGE_STEPS)
+        pool.set_selfplay_nodes(SELFPLAY_NODES)
         pool.step(net, args.preroll)
-    pool.step(net, max(3, args.warmup))
+    pool.reset_stats()
+    pool.step(net, max(3, args.warmup) + 2048)  # (+ 2048 full-budget steps whose evals / moves ratio is kept for positions/s)
+    st_pre = pool.stats()
     pool.reset_stats()
     sampler = ClockSampler(local)
     sampler.start()
@@ -576,6 +585,7 @@ def run_ours(args, rank, world, local, dist):
     clocks = sampler.stop()
     st = pool.stats()
     evals_local = float(st["evals"])
+    evals_per_move = (st_pre["evals"] + st["evals"]) / max(1.0, float(st_pre["moves"] + st["moves"]))
     # phase times (and the roofline's kernel duration): a separate short PROFILED call -- the timed run above records
     # no events and fuses expand + select everywhere (kb_pool_set_profiling is opt-in)
     pool.set_profiling(True)
@@ -752,7 +762,12 @@ def run_ours(args, rank, world, local, dist):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(),
-        "positions_per_sec": moves / (ms * 1e-3),
+        # moves come in bursts (a tree moves every ~870 steps), so a short timed region can hold none: positions/s is
+        # value / (evals per move over the full-budget part of the state preparation + the timed region)
+        "positions_per_sec": value / max(1.0, evals_per_move),
+        "positions_in_timed_region": moves,
+        "evals_per_move": evals_per_move,
+        "skipped_leaves_in_timed_region": int(st["skipped_leaves"]),
         "phase_ms_profiled_call_mean_of_32_steps": phases,
         "roofline": roof,
         "roofline_tree_kernels": roof_tree,

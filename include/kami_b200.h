@@ -187,6 +187,13 @@ int kb_pool_set_step_groups(kb_pool* p, int groups);
 /* phase timing of kb_pool_step (kb_pool_last_phase_ms) is opt-in: when on, up to 32 iterations of a call are bracketed
  * by CUDA events and not fused with their neighbours; off (default) the call records nothing and always fuses */
 int kb_pool_set_profiling(kb_pool* p, int on);
+/* Terminal leaves are absorbed inside `while (n < nodes && !select())` (selfplay.cpp:133); a tree deep in the 50-ply
+ * rule can absorb a hundred of them in one step while every other tree of the batch waits.  With a cap > 0 such a tree
+ * sits the step out after `cap` absorbed visits (its own visit sequence is unchanged; the batch goes out one leaf short;
+ * kb_pool_stats.evals counts real evaluations only).  0 (default) = the reference's batch: always one leaf per tree. */
+int kb_pool_set_terminal_cap(kb_pool* p, int max_terminal_visits);
+/* change the node budget per move of a live pool (bench.py ages its synthetic games quickly with a small budget) */
+int kb_pool_set_selfplay_nodes(kb_pool* p, int nodes);
 /* flush_old_trees (selfplay.cpp:61,119-131): MCTS::reset on every tree, partial trajectories dropped */
 int kb_pool_flush_trees(kb_pool* p);
 
@@ -201,6 +208,7 @@ typedef struct kb_pool_stats {
     uint64_t samples;        /* replay samples emitted */
     uint64_t nodes_in_use;   /* sum over trees */
     uint64_t kernel_launches;/* kernels this pool launched */
+    uint64_t skipped_leaves; /* tree-steps that went out without a leaf (kb_pool_set_terminal_cap) */
 } kb_pool_stats;
 int kb_pool_get_stats(kb_pool* p, kb_pool_stats* out);
 int kb_pool_reset_stats(kb_pool* p);

@@ -51,7 +51,7 @@ class TreeCfg(C.Structure):
 class PoolStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("evals", "moves", "games", "terminal_visits", "children_scanned",
                                           "path_nodes", "children_created", "samples", "nodes_in_use",
-                                          "kernel_launches")]
+                                          "kernel_launches", "skipped_leaves")]
 
 
 class ArenaGame(C.Structure):
@@ -160,6 +160,8 @@ _SIGS = {
     "kb_pool_step_hostio_compact": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "kb_pool_set_step_groups": (C.c_int, [_P, C.c_int]),
     "kb_pool_set_profiling": (C.c_int, [_P, C.c_int]),
+    "kb_pool_set_terminal_cap": (C.c_int, [_P, C.c_int]),
+    "kb_pool_set_selfplay_nodes": (C.c_int, [_P, C.c_int]),
     "kb_pool_flush_trees": (C.c_int, [_P]),
     "kb_current_device": (C.c_int, []),
     "kb_host_register": (C.c_int, [_P, C.c_size_t]),
@@ -539,6 +541,13 @@ class TreePool:
     def set_profiling(self, on):
         """Phase timing of step() (phase_ms) is opt-in; off, step() records nothing and always fuses expand + select."""
         _ck(self.L.kb_pool_set_profiling(self.h, int(bool(on))))
+
+    def set_terminal_cap(self, k):
+        """A tree that absorbed k terminal visits in one step sits the step out (0 = off: the reference's batch)."""
+        _ck(self.L.kb_pool_set_terminal_cap(self.h, int(k)))
+
+    def set_selfplay_nodes(self, nodes):
+        _ck(self.L.kb_pool_set_selfplay_nodes(self.h, int(nodes)))
 
     def flush_trees(self):
         """flush_old_trees (selfplay.cpp:119-131): every tree back to the start position, partial trajectories dropped."""

@@ -130,6 +130,7 @@ struct kb_arena {
     ArenaJob* jobs_dev = nullptr;
     std::vector<ArenaOut> out_host;
     std::vector<int> filed[2];       // trees filed under each network this round, in order (cur_targets / cd_targets)
+    std::vector<char> unfiled;       // tree kept its leaf from an earlier round (its network's batch was full)
     bool pending = false;            // begin() done, end() due
     unsigned long long rounds = 0;
 };
@@ -170,13 +171,29 @@ int arena_begin_impl(kb_arena* a, kb_arena_game* finished, int cap, int* n_finis
                 a->colour[(size_t)i] = mover_turn == a->colour[(size_t)i] ? 1 : -1;
             }
             if (!o.has_leaf) continue;
-            const int root_turn = o.root_ctm == 0 ? 1 : -1, leaf_turn = o.leaf_ctm == 0 ? 1 : -1;
+            const int leaf_turn = o.leaf_ctm == 0 ? 1 : -1;
+            // get_env().turn() before the descent: the root's side to move -- except for a tree that still holds last
+            // round's leaf, whose Env sits AT that leaf (mcts.h:252-254), so the reference reads the leaf's side there
+            const int root_turn = a->unfiled[(size_t)i] ? leaf_turn : (o.root_ctm == 0 ? 1 : -1);
             const int dst = root_turn == a->colour[(size_t)i] ? 1 : 0;  // :68 the buffer, chosen before the descent
             const int dst_slot = (int)a->filed[dst].size();              // :70 and its slot
             const int s = leaf_turn == a->colour[(size_t)i] ? 1 : 0;     // :80-90 the network that is asked
             if ((int)a->filed[s].size() < a->batch) {
                 a->filed[s].push_back(i);
-                if (dst_slot < a->batch) route.push_back(ArenaJob{i, dst, dst_slot, 0});
+                a->unfiled[(size_t)i] = 0;
+                if (dst_slot < a->batch) {
+                    // the reference copies sequentially: a later tree overwrites an earlier one that chose the same slot
+                    // (possible when the earlier leaf was filed under the other network) -- keep one job per slot, the last
+                    bool replaced = false;
+                    for (ArenaJob& j : route)
+                        if (j.which == dst && j.slot == dst_slot) {
+                            j.tree = i;
+                            replaced = true;
+                        }
+                    if (!replaced) route.push_back(ArenaJob{i, dst, dst_slot, 0});
+                }
+            } else {
+                a->unfiled[(size_t)i] = 1;
             }
         }
         i0 = hi;
@@ -240,6 +257,7 @@ int kb_arena_create(kb_arena** out, int games, int batch, int nodes, const kb_tr
     }
     a->colour.assign(colours, colours + games);
     a->out_host.resize((size_t)games);
+    a->unfiled.assign((size_t)games, 0);
     for (int w = 0; w < 2; ++w) {
         KB_CUDA(cudaMalloc(&a->obs_dev[w], sizeof(float) * KB_OBSIZE * (size_t)batch));
         KB_CUDA(cudaMemsetAsync(a->obs_dev[w], 0, sizeof(float) * KB_OBSIZE * (size_t)batch, main_stream()));

@@ -64,7 +64,7 @@ struct TreeCtl {
     u32 root;    // node index of the root in the current space
     u32 alloc;   // nodes used in the current space
     u32 space;   // active semi-space
-    int state;   // 0 idle, 1 leaf waiting for expand()
+    int state;   // 0 idle, 1 leaf waiting for expand(), 2 sat this step out (kb_pool_set_terminal_cap): the next expand is a no-op
     int depth;   // nodes below the root on the current path
     int n_hist;  // game keys in hist[]; path keys follow
     int leaf_nact;
@@ -79,7 +79,7 @@ struct TreeCtl {
 };
 
 struct Stats {
-    unsigned long long evals, moves, games, terminal_visits, children_scanned, path_nodes, children_created, samples;
+    unsigned long long evals, moves, games, terminal_visits, children_scanned, path_nodes, children_created, samples, skipped;
 };
 
 struct PoolDev {
@@ -102,6 +102,7 @@ struct PoolDev {
     Cfg cfg;
     long long* dbg;     // optional [n_trees][8] cycle counters of the last k_pool_select (kb_pool_debug_select_profile)
     int defer_compact;  // batched loops: push only flags a full arena, k_pool_compact (a block per tree) copies
+    int terminal_cap;   // batched select: a tree that absorbed this many terminal visits in one step sits the step out (0 = no cap)
 };
 
 struct WarpScratch {

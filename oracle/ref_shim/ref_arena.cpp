@@ -56,6 +56,13 @@ extern "C" {
 
 // Runs kami::eval (evaluate.cpp:10-160) after srand(seed) with two pseudo-networks (salts) and returns its stdout log
 // followed by "VERDICT 0|1"; options are set through ref_opt_set_* of the core shim's options object (same TU set here).
+// the pseudo-network on its own (tests pin their numpy restatement of it against this)
+void ref_arena_pseudo_infer(uint32_t salt, float* obs, int batch, float* policy, float* value) {
+    kami::NN nn(8, 8, kami::NFEATURES, kami::PSIZE);
+    g_salt[&nn] = salt;
+    nn.infer(obs, batch, policy, value);
+    g_salt.erase(&nn);
+}
 void ref_arena_opt_int(const char* key, int v) { kami::options::setInt(key, v); }
 void ref_arena_opt_float(const char* key, float v) { kami::options::setFloat(key, v); }
 int ref_arena_run(unsigned seed, uint32_t salt_current, uint32_t salt_candidate, char* out, int cap) {

@@ -511,3 +511,39 @@ def test_reference_nndisk_program(kb):
     err = out.stderr.decode()
     assert "mismatch" not in err, err[:400]
     assert "Saved model to __nndisk_TESTMODEL.pt" in out.stdout.decode()
+
+
+def test_terminal_cap_keeps_every_trees_own_sequence(kb):
+    """kb_pool_set_terminal_cap: a tree that absorbed `cap` terminal visits sits the step out.  Each tree's own sequence of
+    visits and moves must be unchanged (value_index_mode 1: no coupling between trees through NN::infer's value indexing),
+    only shifted in time: every replay row the uncapped pool produced in N steps is produced by the capped pool, which
+    needs more steps for the same games and skips leaves on the way."""
+    net, _ = _net(kb, 64, 1, seed=4)
+    kw = dict(noise_weight=0.0, selfplay_nodes=5, alpha_initial=0.0, alpha_decay=1.0, alpha_final=0.0, alpha_cutoff=0, value_index_mode=1,
+              **H.DEF_YML)
+    n, steps = 48, 5000
+    a = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
+    b = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
+    b.set_terminal_cap(1)
+    a.step(net, steps)
+    b.step(net, 2 * steps)
+    sa, sb = a.stats(), b.stats()
+    assert sa["skipped_leaves"] == 0 and sa["evals"] == n * steps
+    assert sb["skipped_leaves"] > 0 and sb["evals"] == n * 2 * steps - sb["skipped_leaves"]
+    assert sa["terminal_visits"] > 100  # the case exists in this run
+
+    def rows(pool):
+        out = []
+        while True:
+            obs, pi, z = pool.drain_samples(512)
+            if not len(z):
+                break
+            out.extend(o.tobytes() + p.tobytes() + np.float32(v).tobytes() for o, p, v in zip(obs, pi, z))
+        return out
+
+    ra, rb = rows(a), rows(b)
+    assert len(ra) > 200 and len(ra) <= 16384 and len(rb) <= 16384
+    from collections import Counter
+
+    missing = Counter(ra) - Counter(rb)
+    assert not missing, "%d of %d rows of the uncapped run are missing from the capped run" % (sum(missing.values()), len(ra))
