@@ -785,14 +785,21 @@ constexpr int FZ_REGION = 2 * SLAB_BYTES;     // 163840
 constexpr int FZ_STAGE = 10240;               // one weight block: n_sub x 128 B <= 10 KB (80 rows)
 constexpr int FZ_NSTAGE = 5;                  // 50 KB of weights in flight
 constexpr int FZ_SMEM = FZ_HDR + FZ_REGION + FZ_NSTAGE * FZ_STAGE;
-constexpr int FZ_EPI_THREADS = 256;
+// EW epilogue warps (8 or 16).  With 16, every warp of a TMEM lane quarter owns ONE M tile of a layer instead of two:
+// the epilogue phases, which alternate with the MMA phases (layer l + 1 needs all of layer l), halve.
 static_assert(FZ_SMEM <= 232448, "fused tower shared memory budget");
 static_assert(FZ_STAGE % 1024 == 0 && FZ_HDR % 1024 == 0, "swizzled operands need 1024-byte aligned bases");
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ FusedParams P) {
+template <int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_constant__ FusedParams P) {
+    constexpr int FZ_EPI_THREADS = 32 * EW, FC_BAR = FZ_EPI_THREADS + 64, PARTS = EW / 4;
+    auto epi_bar = [] { named_bar_sync<FZ_EPI_THREADS>(1); };
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = ptx::uniform_warp_id(), lane = threadIdx.x & 31;
     const uint32_t s0 = ptx::smem_u32(smem);
@@ -801,8 +808,8 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
     const uint32_t p_full = s0 + 8u * 16, t_full = s0 + 8u * 17, act_ready = s0 + 8u * 18, region_clean = s0 + 8u * 19;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
     float* vbuf = reinterpret_cast<float*>(smem + 512);     // [7][64] value-conv outputs
-    float* sbias = reinterpret_cast<float*>(smem + 2560);   // all folded biases (n_bias <= 1400 floats)
-    float* sred = reinterpret_cast<float*>(smem + 2304);    // [8][7] block-reduction scratch of the dense softmax (224 B)
+    float* sbias = reinterpret_cast<float*>(smem + 2816);   // all folded biases (n_bias <= 1340 floats)
+    float* sred = reinterpret_cast<float*>(smem + 2304);    // [EW][7] block-reduction scratch of the dense softmax (<= 448 B)
     uint8_t* region = smem + FZ_HDR;
     const uint32_t region_s = s0 + FZ_HDR;
     const uint32_t ring_s = region_s + FZ_REGION;
@@ -826,8 +833,8 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
         }
         ptx::mbar_init(p_full, 1);
         ptx::mbar_init(t_full, 1);
-        ptx::mbar_init(act_ready, 8);
-        ptx::mbar_init(region_clean, 8);
+        ptx::mbar_init(act_ready, EW);
+        ptx::mbar_init(region_clean, EW);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -946,34 +953,35 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
 #pragma unroll
             for (int s = 0; s < NB; ++s) { o[s][0] = b4.x; o[s][1] = b4.y; o[s][2] = b4.z; o[s][3] = b4.w; }
             const float4* wt = reinterpret_cast<const float4*>(P.fct) + j;  // fct[p][256]
-            float4 wq[16];
+            constexpr int FCB = EW == 8 ? 16 : 8;  // weight rows in flight per round (register budget: 170 / 102 per thread)
+            float4 wq[FCB];
 #pragma unroll
-            for (int p = 0; p < 16; ++p) wq[p] = __ldg(wt + p * 64);  // first quarter of the weights in flight before the wait
-            asm volatile("bar.sync 2, 320;" ::: "memory");
+            for (int p = 0; p < FCB; ++p) wq[p] = __ldg(wt + p * 64);  // first rows in flight before the wait
+            named_bar_sync<FC_BAR>(2);
 #pragma unroll
-            for (int pq = 0; pq < 4; ++pq) {
-                float4 wn[16];
-                if (pq < 3) {
+            for (int pq = 0; pq < 64 / FCB; ++pq) {
+                float4 wn[FCB];
+                if (pq + 1 < 64 / FCB) {
 #pragma unroll
-                    for (int p = 0; p < 16; ++p) wn[p] = __ldg(wt + ((pq + 1) * 16 + p) * 64);
+                    for (int p = 0; p < FCB; ++p) wn[p] = __ldg(wt + ((pq + 1) * FCB + p) * 64);
                 }
 #pragma unroll
-                for (int p = 0; p < 16; ++p) {
+                for (int p = 0; p < FCB; ++p) {
 #pragma unroll
                     for (int s = 0; s < NB; ++s) {
-                        const float v = vbuf[s * 64 + pq * 16 + p];
+                        const float v = vbuf[s * 64 + pq * FCB + p];
                         o[s][0] = fmaf(v, wq[p].x, o[s][0]);
                         o[s][1] = fmaf(v, wq[p].y, o[s][1]);
                         o[s][2] = fmaf(v, wq[p].z, o[s][2]);
                         o[s][3] = fmaf(v, wq[p].w, o[s][3]);
                     }
                 }
-                if (pq < 3) {
+                if (pq + 1 < 64 / FCB) {
 #pragma unroll
-                    for (int p = 0; p < 16; ++p) wq[p] = wn[p];
+                    for (int p = 0; p < FCB; ++p) wq[p] = wn[p];
                 }
             }
-            if (ii + 1 < my_items) asm volatile("bar.arrive 3, 320;" ::: "memory");  // vbuf may be overwritten
+            if (ii + 1 < my_items) named_bar_arrive<FC_BAR>(3);  // vbuf may be overwritten
             else pdl_launch_dependents();
             bool bad = false;
 #pragma unroll
@@ -989,7 +997,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
         }
     } else if (warp >= 4) {
         // ===== epilogue warps =====
-        const int e = warp - 4, q = e & 3, half = e >> 2;
+        const int e = warp - 4, q = e & 3, half = e >> 2;  // half: which of the PARTS tile sets of its lane quarter this warp owns
         const int et = threadIdx.x - 128;  // 0..255
         uint32_t t_phase = 0;
         const bool stamp = P.ts && blockIdx.x == 0 && et == 0;
@@ -1019,7 +1027,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 // The two warps of a lane quarter split the TILES (even / odd), not the columns: the same instruction count
                 // per warp, but half as many dependent TMEM-load -> convert -> store chains for the 64-column tower layers.
 #pragma unroll 1
-                for (int mt = half; mt < 4; mt += 2) {
+                for (int mt = half; mt < 4; mt += PARTS) {
                     const int r = 32 * q + lane;
                     const int R = 16 * mt + (r >> 3), x = r & 7;
                     const int slot = (R - 1) / 9, y = (R - 1) - slot * 9;
@@ -1027,17 +1035,18 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                     const int px = R * TALL_PITCH + 1 + x;
                     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + mt * L.n;
 #pragma unroll 1
-                  for (int cg0 = 0; cg0 < ncg; cg0 += 4) {
-                    const int cg1 = cg0 + 4 < ncg ? cg0 + 4 : ncg;
-                    // up to 4 column groups (64 fp32 columns) per round: issue every TMEM load, wait once
-                    uint32_t v[4][16];
+                  constexpr int RG = EW == 8 ? 4 : 2;  // column groups (16 fp32 columns each) per round: register budget
+                  for (int cg0 = 0; cg0 < ncg; cg0 += RG) {
+                    const int cg1 = cg0 + RG < ncg ? cg0 + RG : ncg;
+                    // up to RG column groups per round: issue every TMEM load, wait once
+                    uint32_t v[RG][16];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
+                    for (int g = 0; g < RG; ++g)
                         if (cg0 + g < cg1) ptx::tmem_ld16(taddr + (cg0 + g) * 16, v[g]);
                     ptx::tmem_ld_wait();
                     if (!valid) continue;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < RG; ++g) {
                         const int cg = cg0 + g;
                         if (cg >= cg1) break;
                         float f[16];
@@ -1094,7 +1103,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 if (l == P.tower_layers - 1) {
                     // ---- value conv 1x1 + ReLU on X (nn.cpp:83-86); the 64 -> 256 Linear + tanh runs on warps 2-3 ----
                     epi_bar();  // X complete
-                    if (ii > 0) asm volatile("bar.sync 3, 320;" ::: "memory");  // vbuf consumed by the previous item's Linear
+                    if (ii > 0) named_bar_sync<FC_BAR>(3);  // vbuf consumed by the previous item's Linear
                     const uint4* X = reinterpret_cast<const uint4*>(region + P.layer[l].dst_off);
                     for (int i = et; i < NB * 64; i += FZ_EPI_THREADS) {
                         const int slot = i >> 6, pix = i & 63;
@@ -1113,7 +1122,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                         }
                         vbuf[i] = fmaxf(acc, 0.0f);
                     }
-                    asm volatile("bar.arrive 2, 320;" ::: "memory");  // vbuf ready for warps 2-3
+                    named_bar_arrive<FC_BAR>(2);  // vbuf ready for warps 2-3
                 }
             }
             // ---- softmax over the 4672 logits of each board (nn.cpp:80) ----
@@ -1150,7 +1159,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 }
             } else {
                 // every thread owns 19 logits of each of the 7 boards; two block-wide reductions in total
-                float* red = sred;  // [8 warps][7] maxima, then [8][7] sums
+                float* red = sred;  // [EW warps][7] maxima, then [EW][7] sums
                 const float* lg = reinterpret_cast<const float*>(region);
                 constexpr int PER = (KB_PSIZE + FZ_EPI_THREADS - 1) / FZ_EPI_THREADS;  // 19
                 float m[NB], sum[NB];
@@ -1170,7 +1179,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 for (int b = 0; b < NB; ++b) {
                     float mm = red[b];
 #pragma unroll
-                    for (int w = 1; w < 8; ++w) mm = fmaxf(mm, red[w * NB + b]);
+                    for (int w = 1; w < EW; ++w) mm = fmaxf(mm, red[w * NB + b]);
                     m[b] = mm;
                 }
                 epi_bar();  // maxima consumed before the sums reuse the scratch
@@ -1191,7 +1200,7 @@ __global__ void __launch_bounds__(384, 1) k_tower64(const __grid_constant__ Fuse
                 for (int b = 0; b < NB; ++b) {
                     float ss = red[b];
 #pragma unroll
-                    for (int w = 1; w < 8; ++w) ss += red[w * NB + b];
+                    for (int w = 1; w < EW; ++w) ss += red[w * NB + b];
                     sum[b] = ss;
                     const int board = item * NB + b;
                     if (board < P.boards) {
@@ -1594,8 +1603,13 @@ static int net_forward_impl(kb_net* net, NetWs& ws, const void* planes, int batc
     const uint4* in = reinterpret_cast<const uint4*>(planes);
     if (net->fused) {
         static bool configured[16] = {};  // function attributes are per device
+        static const int epi_warps = [] {
+            const char* e = getenv("KB_TOWER_EPI_WARPS");
+            return e && atoi(e) == 8 ? 8 : 16;
+        }();
         if (!configured[net->device]) {
-            KB_CUDA(cudaFuncSetAttribute(k_tower64, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
+            KB_CUDA(cudaFuncSetAttribute(k_tower64<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
+            KB_CUDA(cudaFuncSetAttribute(k_tower64<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
             configured[net->device] = true;
         }
         FusedParams fp = net->fp;
@@ -1611,7 +1625,8 @@ static int net_forward_impl(kb_net* net, NetWs& ws, const void* planes, int batc
         fp.items = items_for(batch);
         fp.boards = batch;
         const int grid = fp.items < sm_count() ? fp.items : sm_count();
-        KB_CUDA(launch_pdl(1, k_tower64, dim3(grid), dim3(384), FZ_SMEM, st, fp));
+        if (epi_warps == 16) KB_CUDA(launch_pdl(1, k_tower64<16>, dim3(grid), dim3(128 + 32 * 16), FZ_SMEM, st, fp));
+        else KB_CUDA(launch_pdl(1, k_tower64<8>, dim3(grid), dim3(128 + 32 * 8), FZ_SMEM, st, fp));
         return KB_OK;
     }
     int r;
@@ -1895,7 +1910,7 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
             allb.insert(allb.end(), L.hbias.begin(), L.hbias.end());
         }
         fp.n_bias = (int)allb.size();
-        if (fp.n_bias <= 1400 && fp.n_layers <= 16) {
+        if (fp.n_bias <= 1340 && fp.n_layers <= 16) {
             KB_CUDA(cudaMalloc(&net->fused_w, allw.size() * 2));
             KB_CUDA(cudaMemcpy(net->fused_w, allw.data(), allw.size() * 2, cudaMemcpyHostToDevice));
             KB_CUDA(cudaMalloc(&net->fused_bias, allb.size() * 4));
