@@ -43,7 +43,7 @@ TOWER64_DRAM_BYTES_PER_LAUNCH = 12861440  # profiles/r01_ncu_summary_v3.txt
 # trees are rebuilt under the full budget until every tree has moved a few times at 1024 nodes.
 AGE_STEPS, AGE_NODES = 6000, 32
 PREROLL_STEPS = 3500
-TERMINAL_CAP = 4                    # kb_pool_set_terminal_cap: see include/kami_b200.h
+TERMINAL_CAP = 2                    # kb_pool_set_terminal_cap: see include/kami_b200.h
 METRIC = "selfplay_nn_evals_per_sec"
 UNIT = "evals/s"
 

@@ -192,6 +192,11 @@ int kb_pool_set_profiling(kb_pool* p, int on);
  * sits the step out after `cap` absorbed visits (its own visit sequence is unchanged; the batch goes out one leaf short;
  * kb_pool_stats.evals counts real evaluations only).  0 (default) = the reference's batch: always one leaf per tree. */
 int kb_pool_set_terminal_cap(kb_pool* p, int max_terminal_visits);
+/* Experimental ("split select"): kb_pool_step with a terminal cap publishes every leaf's input planes BEFORE it generates
+ * the leaf's moves, and the tower, already launched, starts on the planes while the move generators still run.  Correct
+ * (tests) but not faster on B200: -1 (default) = off unless KB_SPLIT_SELECT=1; 0 off; 1 on.  A leaf that
+ * turns out to be mate / stalemate then sits its step out. */
+int kb_pool_set_split_select(kb_pool* p, int mode);
 /* change the node budget per move of a live pool (bench.py ages its synthetic games quickly with a small budget) */
 int kb_pool_set_selfplay_nodes(kb_pool* p, int nodes);
 /* flush_old_trees (selfplay.cpp:61,119-131): MCTS::reset on every tree, partial trajectories dropped */
@@ -291,6 +296,24 @@ int kb_trainer_forward_backward_dev(kb_trainer* t, const float* obs_dev, const f
 int kb_trainer_apply_sgd(kb_trainer* t, float lr, float grad_scale);
 /* test hook: one board of a saved training activation, fp32 [channels][64] (which: 0 conv output, 1 layer output) */
 int kb_trainer_debug_activation(kb_trainer* t, int layer, int which, int board, float* out, int* channels);
+
+/* ---- data-parallel training from one host process (BASELINE config 5) ------------------------------------
+ * A kb_trainer replica per GPU, one NCCL all-reduce(sum) of the flat fp32 gradient bucket per mini-batch over NVLink, the
+ * same SGD step on every replica.  NCCL is bound at run time (libnccl.so.2); without it kb_dp_create reports
+ * KB_ERR_UNSUPPORTED and everything else in the library still works. */
+typedef struct kb_dp kb_dp;
+int kb_dp_create(kb_dp** out, const int* devices, int n, int filters, int residuals, int max_batch_per_device);
+int kb_dp_destroy(kb_dp* d);
+int kb_dp_size(kb_dp* d);
+kb_trainer* kb_dp_replica(kb_dp* d, int rank);
+int kb_dp_load_blob(kb_dp* d, const float* blob, size_t n_floats);
+int kb_dp_export_blob(kb_dp* d, int rank, float* blob, size_t n_floats);
+/* rank r takes rows [r * batch_per_device, (r + 1) * batch_per_device) of the host arrays (NN::train's arrays, nn.h:67) */
+int kb_dp_step(kb_dp* d, const float* obs, const float* obs_p, const float* obs_v, int batch_per_device, float lr, float grad_scale, float* loss);
+/* every replica's batch already resident on its own GPU (arrays of n device pointers) */
+int kb_dp_step_dev(kb_dp* d, const float* const* obs_dev, const float* const* obs_p_dev, const float* const* obs_v_dev, int batch_per_device, float lr,
+                   float grad_scale);
+int kb_dp_allreduce_apply(kb_dp* d, float lr, float grad_scale);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     MCTS,
     NN,
     Trainer,
+    DataParallelTrainer,
     TreePool,
     Arena,
     TreeCfg,

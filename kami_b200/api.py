@@ -147,6 +147,15 @@ _SIGS = {
     "kb_pool_leaf_positions": (C.c_int, [_P, _P]),
     "kb_pool_expand": (C.c_int, [_P, _f32p, _f32p, C.c_int]),
     "kb_pool_expand_dev": (C.c_int, [_P, _P, _P, C.c_int]),
+    "kb_dp_create": (C.c_int, [C.POINTER(_P), _i32p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "kb_dp_destroy": (C.c_int, [_P]),
+    "kb_dp_size": (C.c_int, [_P]),
+    "kb_dp_replica": (_P, [_P, C.c_int]),
+    "kb_dp_load_blob": (C.c_int, [_P, _f32p, C.c_size_t]),
+    "kb_dp_export_blob": (C.c_int, [_P, C.c_int, _f32p, C.c_size_t]),
+    "kb_dp_step": (C.c_int, [_P, _f32p, _f32p, _f32p, C.c_int, C.c_float, C.c_float, _f32p]),
+    "kb_dp_step_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_float, C.c_float]),
+    "kb_dp_allreduce_apply": (C.c_int, [_P, C.c_float, C.c_float]),
     "kb_arena_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.POINTER(TreeCfg), _i32p, C.c_int]),
     "kb_arena_destroy": (C.c_int, [_P]),
     "kb_arena_round": (C.c_int, [_P, _P, _P, C.POINTER(ArenaGame), C.c_int, _i32p]),
@@ -162,6 +171,7 @@ _SIGS = {
     "kb_pool_set_profiling": (C.c_int, [_P, C.c_int]),
     "kb_pool_set_terminal_cap": (C.c_int, [_P, C.c_int]),
     "kb_pool_set_selfplay_nodes": (C.c_int, [_P, C.c_int]),
+    "kb_pool_set_split_select": (C.c_int, [_P, C.c_int]),
     "kb_pool_flush_trees": (C.c_int, [_P]),
     "kb_current_device": (C.c_int, []),
     "kb_host_register": (C.c_int, [_P, C.c_size_t]),
@@ -418,6 +428,43 @@ class Trainer:
         return out[:ch.value].copy()
 
 
+class DataParallelTrainer:
+    """NN::train mini-batches data-parallel over the GPUs of the box from this one process (kb_dp_*): a Trainer replica
+    per GPU, one NCCL all-reduce(sum) of the gradient bucket per step, the same SGD step everywhere."""
+
+    def __init__(self, devices, filters, residuals, max_batch_per_device):
+        self.L = lib()
+        self.devices = list(devices)
+        self.filters, self.residuals = filters, residuals
+        dv = np.ascontiguousarray(self.devices, np.int32)
+        self.h = _P()
+        _ck(self.L.kb_dp_create(C.byref(self.h), _ip(dv), len(dv), filters, residuals, max_batch_per_device))
+        self.n = self.L.kb_net_blob_floats(filters, residuals)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.kb_dp_destroy(self.h)
+            self.h = None
+
+    def load_blob(self, blob):
+        blob = np.ascontiguousarray(blob, np.float32)
+        _ck(self.L.kb_dp_load_blob(self.h, _fp(blob), blob.size))
+
+    def export_blob(self, rank=0):
+        out = np.zeros(self.n, np.float32)
+        _ck(self.L.kb_dp_export_blob(self.h, rank, _fp(out), out.size))
+        return out
+
+    def step(self, obs, obs_p, obs_v, lr, grad_scale=1.0):
+        """obs [n_dev * b][1920], obs_p [n_dev * b][4672], obs_v [n_dev * b]; returns the summed loss."""
+        obs = np.ascontiguousarray(obs, np.float32)
+        obs_p = np.ascontiguousarray(obs_p, np.float32)
+        obs_v = np.ascontiguousarray(obs_v, np.float32)
+        loss = C.c_float()
+        _ck(self.L.kb_dp_step(self.h, _fp(obs), _fp(obs_p), _fp(obs_v), len(obs_v) // len(self.devices), float(lr), float(grad_scale), C.byref(loss)))
+        return loss.value
+
+
 class NN:
     """kami::NN: NN(width, height, features, psize) with `filters` / `residuals` taken from the
     arguments instead of the global options map (nn.cpp:42-43)."""
@@ -545,6 +592,10 @@ class TreePool:
     def set_terminal_cap(self, k):
         """A tree that absorbed k terminal visits in one step sits the step out (0 = off: the reference's batch)."""
         _ck(self.L.kb_pool_set_terminal_cap(self.h, int(k)))
+
+    def set_split_select(self, mode):
+        """step() with a terminal cap: planes before move lists, tower started under the move generators (-1 auto, 0 off, 1 on)."""
+        _ck(self.L.kb_pool_set_split_select(self.h, int(mode)))
 
     def set_selfplay_nodes(self, nodes):
         _ck(self.L.kb_pool_set_selfplay_nodes(self.h, int(nodes)))

@@ -776,10 +776,18 @@ struct FusedParams {
     const uint8_t* legal_n;
     unsigned long long legal_stride;
     float* prior;
+    // split select (tree.cuh PoolDev::sync): the producing kernel is still running when this one starts; sync[0] reaches
+    // sync_target when every board's planes are written, sync[1] when every legal-move list is.  nullptr: ordinary
+    // programmatic dependent launch (griddepcontrol.wait = the producing kernel has completed).
+    const unsigned* sync;
+    unsigned sync_target;
     float bv;
     int n_bias, items, boards, n_layers, tower_layers;
     FusedLayer layer[16];
 };
+#ifndef KB_TOWER_PIPE_DEFAULT
+#define KB_TOWER_PIPE_DEFAULT 0
+#endif
 constexpr int FZ_HDR = 8192;                  // barriers, tmem slot, value scratch, biases
 constexpr int FZ_REGION = 2 * SLAB_BYTES;     // 163840
 constexpr int FZ_STAGE = 10240;               // one weight block: n_sub x 128 B <= 10 KB (80 rows)
@@ -846,6 +854,22 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // wait for the producing kernel's data: its completion (PDL), or -- split select -- one of its two progress counters.
+    // Every lane polls with acquire loads (the data is then visible to each of them); bounded, so a lost update cannot hang the GPU.
+    auto wait_input = [&](int which) {
+        if (!P.sync) {
+            pdl_wait();
+            return;
+        }
+        const unsigned* ctr = P.sync + which;
+        for (int tries = 0; tries < (1 << 22); ++tries) {
+            unsigned v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if ((int)(v - P.sync_target) >= 0) break;
+            __nanosleep(40);
+        }
+        __syncwarp();
+    };
 
     if (warp == 0) {
         // ===== producer (converged warp, one elected lane issues) =====
@@ -853,7 +877,10 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             ptx::mbar_wait(region_clean, ii & 1);
-            if (ii == 0) pdl_wait();
+            if (ii == 0) {
+                wait_input(0);
+                if (P.sync) asm volatile("fence.proxy.async;" ::: "memory");  // planes were written by generic stores of a kernel that is still running
+            }
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(p_full, SLAB_BYTES);
                 ptx::bulk_g2s(region_s + SLAB_BYTES, P.planes + (size_t)item * IN_SLABS * SLAB_U4, SLAB_BYTES, p_full);
@@ -884,7 +911,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
         // ===== MMA issuer (converged warp, one elected lane issues) =====
         int stage = 0, sphase = 0;
         uint32_t act_phase = 0;
-        pdl_wait();
+        if (!P.sync) pdl_wait();  // (this role touches nothing of the producing kernel: its inputs arrive through p_full)
         for (int ii = 0; ii < my_items; ++ii) {
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
@@ -945,7 +972,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
         // ===== value head, second half: Linear(64 -> 256) + tanh (nn.cpp:87-88) on the value conv's outputs, off the
         // epilogue warps' critical path (they go on with the policy head meanwhile).  Thread j owns outputs 4j..4j+3. =====
         const int j = threadIdx.x - 64;  // 0..63
-        pdl_wait();
+        wait_input(0);  // the value rows of the previous step are read by the producing kernel's expand phase, which precedes its planes
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.fcb) + j);
@@ -1014,7 +1041,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(region_clean);
             }
-            if (ii == 0) pdl_wait();
+            if (ii == 0 && !P.sync) pdl_wait();
             KB_STAMP();
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
@@ -1130,6 +1157,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
             if (ii + 1 == my_items) pdl_launch_dependents();
             KB_STAMP();
             if (P.legal_act) {
+                if (P.sync) wait_input(1);  // the move lists are the last thing the producing kernel writes
                 // ---- softmax numerators over the legal moves only: warp e gathers board e's logits ----
                 const float* lg = reinterpret_cast<const float*>(region);
                 const int board = item * NB + e;
@@ -1234,6 +1262,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
         P.ts[129 + 2 * blockIdx.x] = t;
     }
 }
+
+#include "tower_pipe.inl"
 
 // valueconv 1x1 (F -> 1) + BN + ReLU, Linear(64 -> 256), tanh (nn.cpp:83-88).  One block per
 // board.  wv / bv: BN-folded conv weights; fct: valuefc.weight transposed to [64][256].
@@ -1436,6 +1466,7 @@ struct kb_net {
     int launches = 0;
     // fused single-kernel path (filters == 64)
     bool fused = false;
+    int tower_pipe = 0;  // fused path: 1 = k_tower64p (per-tile hand-over between layers, tower_pipe.inl), 0 = k_tower64
     kb::FusedParams fp;
     uint4* fused_w = nullptr;
     float* fused_bias = nullptr;
@@ -1585,6 +1616,8 @@ struct LegalRef {
     const uint8_t* nact = nullptr;
     size_t stride = 0;
     float* prior = nullptr;
+    const unsigned* sync = nullptr;
+    unsigned sync_target = 0;
 };
 
 // item0: first item of the activation workspace (X / Y / H) this forward may use, so that forwards of disjoint
@@ -1607,7 +1640,9 @@ static int net_forward_impl(kb_net* net, NetWs& ws, const void* planes, int batc
             const char* e = getenv("KB_TOWER_EPI_WARPS");
             return e && atoi(e) == 8 ? 8 : 16;
         }();
+        const int pipe = net->tower_pipe;
         if (!configured[net->device]) {
+            KB_CUDA(cudaFuncSetAttribute(k_tower64p, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
             KB_CUDA(cudaFuncSetAttribute(k_tower64<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
             KB_CUDA(cudaFuncSetAttribute(k_tower64<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
             configured[net->device] = true;
@@ -1622,15 +1657,22 @@ static int net_forward_impl(kb_net* net, NetWs& ws, const void* planes, int batc
         fp.legal_n = lr.nact;
         fp.legal_stride = lr.stride;
         fp.prior = lr.prior;
+        fp.sync = lr.sync;
+        fp.sync_target = lr.sync_target;
         fp.items = items_for(batch);
         fp.boards = batch;
         const int grid = fp.items < sm_count() ? fp.items : sm_count();
-        if (epi_warps == 16) KB_CUDA(launch_pdl(1, k_tower64<16>, dim3(grid), dim3(128 + 32 * 16), FZ_SMEM, st, fp));
+        if (pipe && !lr.sync) KB_CUDA(launch_pdl(1, k_tower64p, dim3(grid), dim3(FP_THREADS), FZ_SMEM, st, fp));
+        else if (epi_warps == 16) KB_CUDA(launch_pdl(1, k_tower64<16>, dim3(grid), dim3(128 + 32 * 16), FZ_SMEM, st, fp));
         else KB_CUDA(launch_pdl(1, k_tower64<8>, dim3(grid), dim3(128 + 32 * 8), FZ_SMEM, st, fp));
         return KB_OK;
     }
     int r;
     float* logits = policy_dev;
+    if (lr.sync) {
+        set_error("split select needs the fused tower");
+        return KB_ERR_UNSUPPORTED;
+    }
     if (lr.act) {  // the dense logits are scratch in legal mode
         if (item0 != 0) {
             set_error("legal-gather forward of the per-layer path does not support workspace groups");
@@ -1664,9 +1706,13 @@ int net_forward_async(kb_net* net, NetWs& ws, const void* planes, int batch, flo
     return net_forward_impl(net, ws, planes, batch, policy_dev, value256_dev, LegalRef{}, st, item0);
 }
 
+bool net_is_fused(kb_net* net) { return net->fused; }
+
 int net_forward_legal_async(kb_net* net, NetWs& ws, const void* planes, int batch, const void* act_base, const void* nact_base, size_t stride,
-                            float* prior_dev, float* value256_dev, cudaStream_t st, int item0) {
+                            float* prior_dev, float* value256_dev, cudaStream_t st, int item0, const unsigned* sync, unsigned sync_target) {
     LegalRef lr;
+    lr.sync = sync;
+    lr.sync_target = sync_target;
     lr.act = reinterpret_cast<const uint8_t*>(act_base);
     lr.nact = reinterpret_cast<const uint8_t*>(nact_base);
     lr.stride = stride;
@@ -1868,6 +1914,10 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
     cudaFree(net->fused_bias);
     net->fused_w = nullptr;
     net->fused_bias = nullptr;
+    {   // KB_TOWER_PIPE is read when the weights are loaded, so one process can hold both variants (tests compare them)
+        const char* e = getenv("KB_TOWER_PIPE");
+        net->tower_pipe = e ? atoi(e) : KB_TOWER_PIPE_DEFAULT;
+    }
     const char* nofuse = getenv("KB_NO_FUSED_TOWER");
     if (F == 64 && R <= 6 && !(nofuse && nofuse[0] == '1')) {
         std::vector<uint16_t> allw;

@@ -54,7 +54,10 @@ int net_forward_async(kb_net* net, NetWs& ws, const void* planes, int batch, flo
 // result equals the dense softmax followed by that renormalisation.  No [batch][4672] tensor is
 // written.
 int net_forward_legal_async(kb_net* net, NetWs& ws, const void* planes, int batch, const void* act_base, const void* nact_base, size_t stride,
-                            float* prior_dev, float* value256_dev, cudaStream_t stream, int item0 = 0);
+                            float* prior_dev, float* value256_dev, cudaStream_t stream, int item0 = 0, const unsigned* sync = nullptr,
+                            unsigned sync_target = 0);
+// true when `net` runs as the single fused tower kernel (64 filters): only that kernel understands the split select's counters
+bool net_is_fused(kb_net* net);
 int net_launches_per_forward(kb_net* net);
 // fp32 [n][64][30] observations -> bf16 tall-image planes (tree.cu)
 int obs_to_tall_launch(const float* obs_dev, int n, void* planes, cudaStream_t st);

@@ -64,7 +64,7 @@ struct TreeCtl {
     u32 root;    // node index of the root in the current space
     u32 alloc;   // nodes used in the current space
     u32 space;   // active semi-space
-    int state;   // 0 idle, 1 leaf waiting for expand(), 2 sat this step out (kb_pool_set_terminal_cap): the next expand is a no-op
+    int state;   // 0 idle, 1 leaf waiting for expand(), 3 leaf chosen but its move list is still to be generated (split select), 2 sat this step out (kb_pool_set_terminal_cap): the next expand is a no-op
     int depth;   // nodes below the root on the current path
     int n_hist;  // game keys in hist[]; path keys follow
     int leaf_nact;
@@ -102,6 +102,12 @@ struct PoolDev {
     Cfg cfg;
     long long* dbg;     // optional [n_trees][8] cycle counters of the last k_pool_select (kb_pool_debug_select_profile)
     int defer_compact;  // batched loops: push only flags a full arena, k_pool_compact (a block per tree) copies
+    // split select (kb_pool_step, cap mode): a warp publishes its leaf's planes BEFORE it generates the leaf's moves, so the
+    // tower (launched with programmatic dependent launch, already resident) starts on the planes while the move
+    // generators are still running.  sync[0] counts trees whose planes are out, sync[1] trees whose move list is out;
+    // the tower waits for sync_target on [0] before it loads planes and on [1] before it gathers legal-move logits.
+    unsigned* sync;
+    unsigned sync_target;
     int terminal_cap;   // batched select: a tree that absorbed this many terminal visits in one step sits the step out (0 = no cap)
 };
 

@@ -547,3 +547,75 @@ def test_terminal_cap_keeps_every_trees_own_sequence(kb):
 
     missing = Counter(ra) - Counter(rb)
     assert not missing, "%d of %d rows of the uncapped run are missing from the capped run" % (sum(missing.values()), len(ra))
+
+
+def test_tower_variants_agree_bit_for_bit(kb):
+    """k_tower64p (per-tile hand-over between layers, csrc/tower_pipe.inl) against k_tower64 (whole layers): same weights,
+    same arithmetic per accumulator, so dense policy rows, all 256 value outputs and the legal-move priors of a pool step
+    must be identical; checked on ragged batches (1, 7, 8, 300 boards: one CTA with several items included)."""
+    params = NO.init_params(64, 2, seed=21)
+    blob = NO.pack_blob(params, 64, 2)
+    nets = {}
+    for v in ("0", "1"):
+        os.environ["KB_TOWER_PIPE"] = v
+        try:
+            nets[v] = kb.NN(64, 2)
+            nets[v].load_blob(blob)
+        finally:
+            del os.environ["KB_TOWER_PIPE"]
+    obs = np.stack([e.observe() for e in H.sample_positions(300, seed=30)])
+    for b in (1, 7, 8, 300):
+        p0, v0 = nets["0"].forward_full(obs[:b])
+        p1, v1 = nets["1"].forward_full(obs[:b])
+        assert np.array_equal(p0, p1) and np.array_equal(v0, v1), b
+    big = np.ascontiguousarray(np.tile(obs, (7, 1))[:2048])  # 293 items on 148 SMs: two items per CTA
+    p0, v0 = nets["0"].forward_full(big)
+    p1, v1 = nets["1"].forward_full(big)
+    assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+    op, ov = NO.forward(params, obs[:64])
+    assert np.abs(nets["1"].forward_full(obs[:64])[1] - ov).max() <= 1e-2
+    kw = dict(noise_weight=0.05, selfplay_nodes=16, seed=8, alpha_initial=1.0, alpha_final=1.0, **H.DEF_YML)
+    a = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
+    b = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
+    a.step(nets["0"], 60)
+    b.step(nets["1"], 60)
+    for t in range(300):
+        assert a.tree(t).digest() == b.tree(t).digest(), t
+
+
+def test_split_select_keeps_every_trees_own_sequence(kb):
+    """Split select (planes first, move lists under the tower, kb_pool_set_split_select): with the cap on in both pools
+    and no coupling between trees (value_index_mode 1) every tree walks the same sequence of visits and moves; only a
+    leaf that turns out to be mate / stalemate costs the split pool a step.  Every replay row of the unsplit pool must
+    come out of the split pool (which runs a little longer), and the two agree on what they counted."""
+    from collections import Counter
+
+    net, _ = _net(kb, 64, 1, seed=4)
+    kw = dict(noise_weight=0.05, selfplay_nodes=6, alpha_initial=1.0, alpha_decay=0.97, alpha_final=0.6, alpha_cutoff=30, value_index_mode=1,
+              seed=12, **H.DEF_YML)
+    n, steps = 40, 1600  # ~10 k replay rows: below the 16 384-row device ring in both pools
+    a = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
+    b = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
+    for pool, mode in ((a, 0), (b, 1)):
+        pool.set_terminal_cap(2)
+        pool.set_split_select(mode)
+    a.step(net, steps)
+    for _ in range(5):
+        b.step(net, steps // 4)
+    sa, sb = a.stats(), b.stats()
+    assert sa["evals"] == n * steps - sa["skipped_leaves"] and sb["evals"] == n * (steps // 4) * 5 - sb["skipped_leaves"]
+    assert sb["games"] >= sa["games"] > 8
+
+    def rows(pool):
+        out = []
+        while True:
+            obs, pi, z = pool.drain_samples(512)
+            if not len(z):
+                break
+            out.extend(o.tobytes() + p.tobytes() + np.float32(v).tobytes() for o, p, v in zip(obs, pi, z))
+        return out
+
+    ra, rb = rows(a), rows(b)
+    assert 200 < len(ra) < 16384 and len(rb) < 16384
+    missing = Counter(ra) - Counter(rb)
+    assert not missing, "%d of %d rows of the unsplit run are missing from the split run" % (sum(missing.values()), len(ra))

@@ -97,3 +97,42 @@ def test_train_loop_reduces_loss_and_feeds_inference(kb):
     pol, val = net.forward_full(obs[:8])
     op, ov = NO.forward(p, obs[:8])
     assert np.abs(val - ov).max() <= 3e-2 and np.abs(pol.sum(1) - 1).max() < 1e-4
+
+
+def test_data_parallel_step_from_one_process(kb):
+    """kb_dp_*: a trainer replica per GPU (as many as the box has, at most 2 here), one NCCL all-reduce(sum) of the
+    gradient bucket, the same SGD step on every replica -- against two independent single-GPU trainers whose gradients
+    are added on the host.  Sums of two fp32 values are order-independent, so with 2 ranks the weights must agree to the
+    last bit of the SGD arithmetic; replicas must be bit-identical to each other."""
+    F, R, b = 64, 1, 12
+    ndev = min(2, kb.device_count())
+    params = NO.init_params(F, R, seed=4)
+    blob = NO.pack_blob(params, F, R)
+    obs, pi, z = _batch(b * ndev, seed=70)
+    dp = kb.DataParallelTrainer(list(range(ndev)), F, R, b)
+    dp.load_blob(blob)
+    lr = 0.002
+    loss = dp.step(obs, pi, z, lr)
+    got = [dp.export_blob(r) for r in range(ndev)]
+    for r in range(1, ndev):
+        assert np.array_equal(got[0], got[r]), "replicas diverged"
+    total = np.zeros_like(blob)
+    want_loss = 0.0
+    for r in range(ndev):
+        tr = kb.Trainer(F, R, b)
+        tr.load_blob(blob)
+        want_loss += tr.forward_backward(obs[r * b:(r + 1) * b], pi[r * b:(r + 1) * b], z[r * b:(r + 1) * b])
+        total += tr.export_grads()
+        stats = tr.export_blob()
+    assert abs(loss - want_loss) <= 1e-3 * abs(want_loss)
+    # trainable tensors: w - lr * sum of gradients (running statistics are per replica: compare the trainable part only)
+    off = 0
+    for name, shape in NO.param_order(F, R):
+        n = int(np.prod(shape))
+        if TO.trainable(name):
+            want = blob[off:off + n] - np.float32(lr) * total[off:off + n]
+            assert np.abs(got[0][off:off + n] - want).max() <= 2e-6 * max(1.0, float(np.abs(want).max())), name
+        off += n
+    # a second step runs (communicator reuse) and moves the weights again
+    dp.step(obs, pi, z, lr)
+    assert not np.array_equal(dp.export_blob(0), got[0])
