@@ -35,7 +35,7 @@ TREES_PER_GPU = 1024
 FILTERS, RESIDUALS = 64, 2          # options.def.yml:29,53
 SELFPLAY_NODES = 1024               # options.def.yml selfplay_nodes
 NODE_CAPACITY = 1 << 19  # 2 x 10 MB per tree: the copying collector runs about once per 40 moves
-TOWER64_DRAM_BYTES_PER_LAUNCH = 12861440  # profiles/r01_ncu_summary_v3.txt
+TOWER64_DRAM_BYTES_PER_LAUNCH = 12852992  # dram__bytes_read.sum + dram__bytes_write.sum of one k_tower64<16> launch, profiles/r02_ncu_summary.txt
 # State preparation (untimed).  The step gets slower as the synthetic games leave the opening (more legal moves per
 # position, terminal leaves to absorb: 84 us/step after 5 k steps from fresh trees, 118-135 us from 20 k steps on,
 # tools/steady_state.py), so the timed region must not start from young games.  The games are aged quickly with a small
@@ -599,12 +599,12 @@ def run_ours(args, rank, world, local, dist):
     # roofline of the dominant kernel of the step (timed live with CUDA events inside kb_pool_step)
     t_f, h_f = net.flops()
     phases = {"select+encode": ph["select"], "tower+heads": ph["tower"], "expand+backup": ph["expand"]}
-    # dominant kernel of the step: k_tower64 (58 % of the step in the ncu launch list, profiles/r01_ncu_summary_v3.txt)
+    # dominant kernel of the step: k_tower64<16> (60 % of the step in the ncu launch list, profiles/r02_ncu_summary.txt)
     achieved = (t_f + h_f) * TREES_PER_GPU / (ph["tower"] * 1e-3) / 1e12
     roof = {"kernel": "k_tower64 (one fused tcgen05 launch: %dx%d tower + policy/value heads + legal-move softmax)" % (RESIDUALS, FILTERS),
             "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one k_tower64 launch at 1024 boards, from the
-            # ncu --set full capture summarised in profiles/r01_ncu_summary_v3.txt (12.861 MB read: 147 input
+            # dram__bytes_read.sum + dram__bytes_write.sum of one k_tower64<16> launch at 1024 boards, from the
+            # ncu --set full capture summarised in profiles/r02_ncu_summary.txt (12.85 MB read: 147 input
             # slabs of 80 KB + weights)
             "traffic": TOWER64_DRAM_BYTES_PER_LAUNCH if TREES_PER_GPU == 1024 else None,
             "traffic_unit": "bytes/launch", "peak_kind": peak_kind + " burst",
@@ -614,8 +614,8 @@ def run_ours(args, rank, world, local, dist):
     per_step += 3904.0 * TREES_PER_GPU
     dur = (ph["select"] + ph["expand"]) * 1e-3
     roof_tree = {"kernel": "k_pool_select + k_pool_expand", "bound": "hbm", "achieved": per_step / dur / 1e9, "peak": hbm_peak,
-                 "unit": "GB/s", "frac": per_step / dur / 1e9 / hbm_peak, "traffic": 2318592 + 1124096,
-                 "traffic_unit": "bytes/step (ncu, select + expand)", "peak_kind": peak_kind,
+                 "unit": "GB/s", "frac": per_step / dur / 1e9 / hbm_peak, "traffic": 3878656,
+                 "traffic_unit": "bytes/step (ncu, k_pool_expand_select, profiles/r02_ncu_summary.txt)", "peak_kind": peak_kind,
                  "algorithmic": "12 B x children scanned + 16 B x path nodes + 16 B x children created + 3904 B planes per leaf"}
 
     # end to end through the reference-shaped host-buffer API (pinned host memory)

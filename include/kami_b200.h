@@ -275,6 +275,9 @@ int kb_host_unregister(void* ptr);
 int kb_timer_start(void);
 int kb_timer_stop(float* ms);
 int kb_flush_l2(size_t bytes);
+/* capture window for profilers started with "profile from start off" (cudaProfilerStart / cudaProfilerStop) */
+int kb_profiler_start(void);
+int kb_profiler_stop(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Training step: NN::train's mini-batch (kami/nn/nn.cpp:224-377) = NNModule::forward in

@@ -127,7 +127,7 @@ class Selfplay {
         int source_generation = model->get_generation();                          // selfplay.cpp:103
         long long flushed = 0;
         kb_pool_stats seen = {};
-        const int iters_per_call = options::getInt("b200_iters_per_call", 64);
+        const int iters_per_call = options::getInt("b200_iters_per_call", 256);
         std::vector<int32_t> game_actions(4096);
         bool game_requested = false;
         auto partial = partial_trajectories.begin();

@@ -196,6 +196,8 @@ _SIGS = {
     "kb_timer_start": (C.c_int, []),
     "kb_timer_stop": (C.c_int, [_f32p]),
     "kb_flush_l2": (C.c_int, [C.c_size_t]),
+    "kb_profiler_start": (C.c_int, []),
+    "kb_profiler_stop": (C.c_int, []),
 }
 ABI_SYMBOLS = tuple(sorted(_SIGS))
 

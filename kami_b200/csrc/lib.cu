@@ -17,6 +17,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_profiler_api.h>
+
 #include "common.cuh"
 
 namespace kb {
@@ -244,6 +246,15 @@ int kb_timer_stop(float* ms) {
     KB_CUDA(cudaEventRecord(g_ev[1], main_stream()));
     KB_CUDA(cudaEventSynchronize(g_ev[1]));
     KB_CUDA(cudaEventElapsedTime(ms, g_ev[0], g_ev[1]));
+    return KB_OK;
+}
+// capture window for `ncu --profile-from-start off` / nsys (tools/prof_step.py)
+int kb_profiler_start(void) {
+    KB_CUDA(cudaProfilerStart());
+    return KB_OK;
+}
+int kb_profiler_stop(void) {
+    KB_CUDA(cudaProfilerStop());
     return KB_OK;
 }
 // writes `bytes` of a scratch buffer on the library stream (L2 flush between timed iterations)

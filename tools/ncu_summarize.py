@@ -8,7 +8,12 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
            "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size", "launch__cluster_size", "launch__registers_per_thread",
-           "launch__shared_mem_per_block_dynamic"]
+           "launch__shared_mem_per_block_dynamic",
+           # shared-memory side (round 2): tensor-core operand reads (1 wavefront = 128 B, 1 per clock per SM at peak), LSU traffic, uniform pipe
+           "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+           "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
 
 
 def launches(path):
