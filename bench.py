@@ -748,14 +748,17 @@ def run_ours(args, rank, world, local, dist):
         L.kb_host_free_pinned(p)
     del pool
     if not args.no_extras:
-        # one C++ host process driving all N GPUs through kami::Selfplay (the other ranks idle at the barrier)
+        # one C++ host process driving all N GPUs through kami::Selfplay.  The other ranks wait on a HOST-side (gloo)
+        # barrier: an NCCL barrier would spin a kernel on their GPUs, which the C++ process is using
+        host_group = dist.new_group(backend="gloo") if dist is not None else None
         barrier(dist, local)
         if rank == 0:
             try:
                 extras["e2e_selfplay_cpp"] = selfplay_cpp_leg(world)
             except Exception as e:
                 extras["e2e_selfplay_cpp"] = {"error": str(e)[:200]}
-        barrier(dist, local)
+        if dist is not None:
+            dist.barrier(group=host_group)
     if rank != 0:
         return
     out = {

@@ -297,6 +297,10 @@ int kb_trainer_grad_buffer(kb_trainer* t, void** dev_ptr, size_t* n_floats);
 int kb_trainer_forward_backward(kb_trainer* t, const float* obs, const float* obs_p, const float* obs_v, int batch, float* loss);
 int kb_trainer_forward_backward_dev(kb_trainer* t, const float* obs_dev, const float* obs_p_dev, const float* obs_v_dev, int batch, float* loss);
 int kb_trainer_apply_sgd(kb_trainer* t, float lr, float grad_scale);
+/* the flat parameter vector on the device (blob order) and the (offset, count) ranges of it that hold BatchNorm running
+ * statistics: data-parallel hosts average those over the replicas, the rest moves by the all-reduced gradient */
+int kb_trainer_param_buffer(kb_trainer* t, void** dev_ptr, size_t* n_floats);
+int kb_trainer_stat_ranges(kb_trainer* t, size_t* offsets, size_t* counts, int cap, int* n);
 /* test hook: one board of a saved training activation, fp32 [channels][64] (which: 0 conv output, 1 layer output) */
 int kb_trainer_debug_activation(kb_trainer* t, int layer, int which, int board, float* out, int* channels);
 

@@ -207,13 +207,29 @@ class NN {
         const int epochs = options::getInt("training_epochs", 8);
         const int tbatch = options::getInt("training_batchsize", 8);
         const size_t osz = (size_t)width * height * features;
+        // b200_train_devices = N > 1: the mini-batch is split over the first N GPUs of the box (kb_dp_*: a trainer replica per
+        // GPU, one NCCL all-reduce of the gradient bucket per mini-batch over NVLink, the same SGD step everywhere).  The
+        // reference trains on one device; with N = 1 (default) so does this, row for row.
+        int ndev = options::getInt("b200_train_devices", 1);
+        if (ndev < 1 || tbatch % ndev != 0) ndev = 1;
         kb_trainer* tr = nullptr;
-        check(kb_trainer_create(&tr, filters, residuals, tbatch));
+        kb_dp* dp = nullptr;
+        if (ndev > 1) {
+            std::vector<int> devs(ndev);
+            for (int i = 0; i < ndev; ++i) devs[i] = i;
+            check(kb_dp_create(&dp, devs.data(), ndev, filters, residuals, tbatch / ndev));
+        } else {
+            check(kb_trainer_create(&tr, filters, residuals, tbatch));
+        }
         struct Guard {
             kb_trainer* t;
-            ~Guard() { kb_trainer_destroy(t); }
-        } guard{tr};
-        check(kb_trainer_load_blob(tr, blob.data(), blob.size()));
+            kb_dp* d;
+            ~Guard() {
+                kb_trainer_destroy(t);
+                kb_dp_destroy(d);
+            }
+        } guard{tr, dp};
+        check(dp ? kb_dp_load_blob(dp, blob.data(), blob.size()) : kb_trainer_load_blob(tr, blob.data(), blob.size()));
         std::vector<int> picker(trajectories);
         for (int i = 0; i < trajectories; ++i) picker[i] = i;
         auto rng = std::default_random_engine{};
@@ -236,9 +252,13 @@ class NN {
                     for (float v : next_input)
                         if (v != v) throw std::runtime_error("training input contains NaN");
                 float loss = 0.0f;
-                check(kb_trainer_forward_backward(tr, next_input.data(), next_policy.data(), next_value.data(), tbatch, &loss));
+                if (dp) {
+                    check(kb_dp_step(dp, next_input.data(), next_policy.data(), next_value.data(), tbatch / ndev, lr, 1.0f, &loss));
+                } else {
+                    check(kb_trainer_forward_backward(tr, next_input.data(), next_policy.data(), next_value.data(), tbatch, &loss));
+                }
                 if (detect_anomaly && loss != loss) throw std::runtime_error("forward output contains NaN");
-                check(kb_trainer_apply_sgd(tr, lr, 1.0f));
+                if (!dp) check(kb_trainer_apply_sgd(tr, lr, 1.0f));
                 avgloss += loss;
                 if (!nbatches) epfirst = loss;
                 eplast = loss;
@@ -252,7 +272,7 @@ class NN {
         ++generation;
         std::cout << "Generated model " << generation << ", average loss " << firstloss << " to " << lastloss << " over " << epochs << " epochs\n";
         std::vector<float> b(blob.size());
-        check(kb_trainer_export_blob(tr, b.data(), b.size()));
+        check(dp ? kb_dp_export_blob(dp, 0, b.data(), b.size()) : kb_trainer_export_blob(tr, b.data(), b.size()));
         check(kb_net_load_blob(net, b.data(), b.size()));
         refresh_replicas(b);
         blob.swap(b);

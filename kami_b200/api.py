@@ -123,6 +123,8 @@ _SIGS = {
                                               C.POINTER(C.c_float)]),
     "kb_trainer_forward_backward_dev": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "kb_trainer_apply_sgd": (C.c_int, [_P, C.c_float, C.c_float]),
+    "kb_trainer_param_buffer": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "kb_trainer_stat_ranges": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int, _i32p]),
     "kb_trainer_debug_activation": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "kb_net_debug_activation": (C.c_int, [_P, C.c_int, C.c_int, _f32p, _i32p]),
     "kb_net_debug_timestamps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_longlong), C.c_int, _i32p]),

@@ -17,7 +17,7 @@ namespace {
 
 typedef struct ncclComm* ncclComm_t;
 typedef int ncclResult_t;
-constexpr int kNcclFloat = 7, kNcclSum = 0;  // ncclFloat32, ncclSum (nccl.h)
+constexpr int kNcclFloat = 7, kNcclSum = 0, kNcclAvg = 4;  // ncclFloat32, ncclSum, ncclAvg (nccl.h)
 struct Nccl {
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -61,7 +61,8 @@ struct kb_dp {
     std::vector<int> devices;
     std::vector<kb_trainer*> tr;
     std::vector<ncclComm_t> comm;
-    std::vector<float*> grads;
+    std::vector<float*> grads, params;
+    std::vector<size_t> stat_off, stat_cnt;  // BatchNorm running statistics inside the parameter vector (same for every replica)
     size_t n_floats = 0;
     int home = 0;  // device the calling thread was bound to at creation (restored after every call)
 };
@@ -92,6 +93,16 @@ int kb_dp_create(kb_dp** out, const int* devices, int n, int filters, int residu
         if ((r = kb_trainer_grad_buffer(t, &g, &nf))) break;
         d->grads.push_back((float*)g);
         d->n_floats = nf;
+        if ((r = kb_trainer_param_buffer(t, &g, &nf))) break;
+        d->params.push_back((float*)g);
+        if (i == 0) {
+            d->stat_off.resize(256);
+            d->stat_cnt.resize(256);
+            int ns = 0;
+            if ((r = kb_trainer_stat_ranges(t, d->stat_off.data(), d->stat_cnt.data(), 256, &ns))) break;
+            d->stat_off.resize((size_t)ns);
+            d->stat_cnt.resize((size_t)ns);
+        }
     }
     if (r == KB_OK) {
         d->comm.resize((size_t)n);
@@ -171,8 +182,9 @@ int kb_dp_step_dev(kb_dp* d, const float* const* obs_dev, const float* const* ob
     kb_init(d->home);
     return r;
 }
-// gradients of all replicas -> their sum on every replica (one NCCL all-reduce per step), then SGD everywhere; returns
-// when every GPU has finished
+// gradients of all replicas -> their sum on every replica (one NCCL all-reduce of the whole bucket, plus the few hundred
+// floats of BatchNorm running statistics averaged in the same NCCL group), then SGD everywhere; returns when every GPU
+// has finished
 int kb_dp_allreduce_apply(kb_dp* d, float lr, float grad_scale) {
     KB_ARG(d, "dp");
     const int n = (int)d->tr.size();
@@ -192,6 +204,18 @@ int kb_dp_allreduce_apply(kb_dp* d, float lr, float grad_scale) {
                 return KB_ERR_CUDA;
             }
         }
+        // BatchNorm running statistics were updated from each replica's own rows: average them, so that the replicas stay
+        // bit-identical and any of them can be exported (torch's DistributedDataParallel broadcasts rank 0's instead)
+        for (size_t k = 0; k < d->stat_off.size(); ++k)
+            for (int i = 0; i < n; ++i) {
+                float* ptr = d->params[(size_t)i] + d->stat_off[k];
+                ncclResult_t nr = nccl()->AllReduce(ptr, ptr, d->stat_cnt[k], kNcclFloat, kNcclAvg, d->comm[(size_t)i], st[(size_t)i]);
+                if (nr != 0) {
+                    nccl()->GroupEnd();
+                    set_error("ncclAllReduce (statistics) failed: %s", nccl()->GetErrorString ? nccl()->GetErrorString(nr) : "NCCL error");
+                    return KB_ERR_CUDA;
+                }
+            }
         KB_NCCL(nccl()->GroupEnd());
     }
     for (int i = 0; i < n; ++i) {

@@ -1324,6 +1324,40 @@ int kb_trainer_debug_activation(kb_trainer* t, int layer, int which, int board, 
     return KB_OK;
 }
 
+// Where the BatchNorm running statistics sit in the flat parameter vector: (offset, count) per layer -- running_mean and
+// running_var are adjacent.  Data-parallel hosts average these ranges over the replicas (kb_dp_*), everything else in the
+// vector is trainable and moves by the all-reduced gradient.
+int kb_trainer_stat_ranges(kb_trainer* t, size_t* offsets, size_t* counts, int cap, int* n) {
+    KB_ARG(t && offsets && counts && n, "trainer / out");
+    int k = 0;
+    for (const TConv& c : t->conv)
+        if (c.bn) {
+            if (k < cap) {
+                offsets[k] = c.rm_off;
+                counts[k] = 2 * (size_t)c.O;
+            }
+            ++k;
+        }
+    if (k < cap) {
+        offsets[k] = t->vrm_off;
+        counts[k] = 2;
+    }
+    ++k;
+    *n = k;
+    if (k > cap) {
+        set_error("%d statistic ranges, caller's arrays hold %d", k, cap);
+        return KB_ERR_CAPACITY;
+    }
+    return KB_OK;
+}
+int kb_trainer_param_buffer(kb_trainer* t, void** dev_ptr, size_t* n_floats) {
+    KB_ARG(t && dev_ptr && n_floats, "trainer / out");
+    KB_BIND(t);
+    *dev_ptr = t->params;
+    *n_floats = t->n_floats;
+    return KB_OK;
+}
+
 // plain SGD (nn.cpp:239-241): w -= lr * grad_scale * grad, then the bf16 operand blocks are rebuilt
 int kb_trainer_apply_sgd(kb_trainer* t, float lr, float grad_scale) {
     KB_REQUIRE_INIT();
