@@ -375,10 +375,25 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_tower64p(const __grid_constan
         KB_STAMP();
         for (int ii = 0; ii < my_items; ++ii) {
             const int item = (int)blockIdx.x + ii * (int)gridDim.x;
-            {   // pads must read as zero: clear the whole region, then hand it to the async proxy
-                uint4* r4 = reinterpret_cast<uint4*>(region);
+            {   // The 3x3 layers read the pad pixels (the row above each board, the column on each side) as zero.  Y gets its
+                // pads with the input slab (the TMA copy below brings the whole slab, pads included, and no epilogue ever
+                // writes a pad); X's pads were overwritten by the previous item's logits, or never initialised: clear those
+                // 192 pixel lines (24 KB) -- not the whole 160 KB region, which cost 6 k cycles at the head of every item.
+                uint4* x4 = reinterpret_cast<uint4*>(region);  // X slab = region offset 0
                 const uint4 z = make_uint4(0, 0, 0, 0);
-                for (int i = et; i < FZ_REGION / 16; i += FZ_EPI_THREADS) r4[i] = z;
+                for (int i = et; i < 192 * 8; i += FZ_EPI_THREADS) {
+                    const int pp = i >> 3, j = i & 7;
+                    int row, col;
+                    if (pp < 80) {  // the 8 pad rows 0, 9, ..., 63
+                        row = (pp / TALL_PITCH) * 9;
+                        col = pp - (pp / TALL_PITCH) * TALL_PITCH;
+                    } else {        // columns 0 and 9 of the 56 board rows
+                        const int qq = pp - 80, br = qq >> 1;
+                        row = 1 + (br >> 3) * 9 + (br & 7);
+                        col = (qq & 1) ? TALL_PITCH - 1 : 0;
+                    }
+                    x4[(row * TALL_PITCH + col) * 8 + j] = z;
+                }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(region_clean);

@@ -6,6 +6,7 @@ api.init(0); L=kami_b200.lib()
 net = kami_b200.NN(64,2); net.load_blob(bench.random_blob(64,2,1))
 kw = dict(noise_weight=0.05, selfplay_nodes=1024, alpha_initial=1.0, alpha_decay=0.95, alpha_final=0.5, alpha_cutoff=20, draw_value_pct=50, **kami_b200.DEF_YML)
 pool = kami_b200.TreePool(1024, 1<<19, api.tree_cfg(seed=1000, **kw))
+pool.set_terminal_cap(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 pool.step(net, int(sys.argv[1]) if len(sys.argv) > 1 else 1536)
 L.kb_pool_debug_select_profile(pool.h, 1, None, 0)
 buf=np.zeros((1024,8),np.int64)
