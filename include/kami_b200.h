@@ -190,7 +190,8 @@ int kb_pool_set_profiling(kb_pool* p, int on);
 /* Terminal leaves are absorbed inside `while (n < nodes && !select())` (selfplay.cpp:133); a tree deep in the 50-ply
  * rule can absorb a hundred of them in one step while every other tree of the batch waits.  With a cap > 0 such a tree
  * sits the step out after `cap` absorbed visits (its own visit sequence is unchanged; the batch goes out one leaf short;
- * kb_pool_stats.evals counts real evaluations only).  0 (default) = the reference's batch: always one leaf per tree. */
+ * kb_pool_stats.evals counts real evaluations only; with NN::infer's value indexing, value_index_mode 0, a tree that sits
+ * out leaves its board's previous planes in the batch).  0 (default) = the reference's batch: always one leaf per tree. */
 int kb_pool_set_terminal_cap(kb_pool* p, int max_terminal_visits);
 /* Experimental ("split select"): kb_pool_step with a terminal cap publishes every leaf's input planes BEFORE it generates
  * the leaf's moves, and the tower, already launched, starts on the planes while the move generators still run.  Correct

@@ -1803,7 +1803,8 @@ extern "C" {
 int kb_net_create(kb_net** out, int filters, int residuals) {
     KB_REQUIRE_INIT();
     KB_ARG(out, "out");
-    KB_ARG(filters == 64 || filters == 128 || filters == 192 || filters == 256, "filters must be a multiple of 64 up to 256");
+    // (the same set kb_trainer_create takes: output-channel passes are 64 or 128 wide, so 192 has no kernel on either side)
+    KB_ARG(filters == 64 || filters == 128 || filters == 256, "filters must be 64, 128 or 256");
     KB_ARG(residuals >= 0 && residuals <= 64, "residuals in [0, 64]");
     kb_net* n = new (std::nothrow) kb_net();
     if (!n) return KB_ERR_ARG;
