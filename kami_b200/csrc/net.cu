@@ -15,6 +15,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -1491,6 +1492,8 @@ struct kb_net {
     // host-pointer calls (kb_net_infer / kb_net_forward_full): one private context per call in flight
     std::mutex ctx_mu;
     std::vector<InferCtx*> ctx_free;
+    std::vector<InferCtx*> ctx_kept;  // contexts host threads keep for kb_net_forward_dev (freed with the net)
+    unsigned long long uid = 0;       // distinguishes this net from an earlier one at the same address (thread-local caches)
     InferCtx* dbg_ctx = nullptr;  // context of the last kb_net_forward_full (kb_net_debug_activation reads it)
 };
 
@@ -1811,6 +1814,8 @@ int kb_net_create(kb_net** out, int filters, int residuals) {
     n->filters = filters;
     n->residuals = residuals;
     n->device = current_device();
+    static std::atomic<unsigned long long> next_uid{1};
+    n->uid = next_uid.fetch_add(1);
     *out = n;
     return KB_OK;
 }
@@ -1833,6 +1838,7 @@ int kb_net_destroy(kb_net* n) {
     }
     cudaFree(n->wv); cudaFree(n->fct); cudaFree(n->fcb);
     for (InferCtx* c : n->ctx_free) ctx_free(c);
+    for (InferCtx* c : n->ctx_kept) ctx_free(c);
     cudaFree(n->fused_w); cudaFree(n->fused_bias); cudaFree(n->ts_dev);
     delete n;
     return KB_OK;
@@ -2015,7 +2021,7 @@ static void ctx_give(kb_net* net, InferCtx* c) {
     net->ctx_free.push_back(c);
 }
 static thread_local InferCtx* tl_dev_ctx = nullptr;  // kb_net_forward_dev: one workspace per host thread, kept
-static thread_local kb_net* tl_dev_ctx_net = nullptr;
+static thread_local unsigned long long tl_dev_ctx_uid = 0;
 
 int kb_net_forward_dev(kb_net* net, const void* planes_dev, int batch, float* policy_dev, float* value256_dev) {
     KB_REQUIRE_INIT();
@@ -2023,10 +2029,12 @@ int kb_net_forward_dev(kb_net* net, const void* planes_dev, int batch, float* po
     int r = bind_device(net->device);
     if (r) return r;
     NetReadGuard lock(net);
-    if (tl_dev_ctx_net != net || !tl_dev_ctx) {
+    if (tl_dev_ctx_uid != net->uid || !tl_dev_ctx) {
         tl_dev_ctx = ctx_take(net);  // (kept by this thread for the life of the net: device-resident benches call this in loops)
-        tl_dev_ctx_net = net;
         if (!tl_dev_ctx) return KB_ERR_ARG;
+        tl_dev_ctx_uid = net->uid;
+        std::lock_guard<std::mutex> g(net->ctx_mu);
+        net->ctx_kept.push_back(tl_dev_ctx);
     }
     if ((r = ws_reserve(tl_dev_ctx->ws, net, batch, main_stream()))) return r;
     return net_forward_async(net, tl_dev_ctx->ws, planes_dev, batch, policy_dev, value256_dev, main_stream());
