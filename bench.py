@@ -43,7 +43,7 @@ TOWER64_DRAM_BYTES_PER_LAUNCH = 12852992  # dram__bytes_read.sum + dram__bytes_w
 # trees are rebuilt under the full budget until every tree has moved a few times at 1024 nodes.
 AGE_STEPS, AGE_NODES = 6000, 32
 PREROLL_STEPS = 3500
-TERMINAL_CAP = 2                    # kb_pool_set_terminal_cap: see include/kami_b200.h
+TERMINAL_CAP = 1                    # kb_pool_set_terminal_cap: see include/kami_b200.h
 METRIC = "selfplay_nn_evals_per_sec"
 UNIT = "evals/s"
 

@@ -120,7 +120,7 @@ class Selfplay {
         kb_check(kb_pool_create(&pool, ibatch, options::getInt("b200_node_capacity", 1 << 18), &cfg));
         // a tree that absorbed this many terminal visits in one step sits the step out instead of holding up the whole
         // batch (include/kami_b200.h kb_pool_set_terminal_cap); 0 = the reference's batch, always one leaf per tree
-        kb_check(kb_pool_set_terminal_cap(pool, options::getInt("b200_terminal_cap", 2)));
+        kb_check(kb_pool_set_terminal_cap(pool, options::getInt("b200_terminal_cap", 1)));
         const int DRAIN = 256;  // replay rows fetched per call (one device -> host copy per call)
         std::vector<float> obs((size_t)DRAIN * OBSIZE), pi((size_t)DRAIN * PSIZE), z(DRAIN);
         const bool flush_old_trees = options::getInt("flush_old_trees", 1) != 0;  // selfplay.cpp:61
