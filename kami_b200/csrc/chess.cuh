@@ -275,6 +275,42 @@ KB_HD bool make_move(const Pos& cur, u16 mv, Pos& next) {
     return true;
 }
 
+// The return value of make_move<false>(p, mv, next) -- "the mover's king is safe afterwards" (position.c:316-319) --
+// without building `next`: the king's attackers are looked up in p's own bitboards under the occupancy the move leaves
+// behind (source emptied, destination filled, en-passant victim removed, castling rook relocated), with the captured
+// piece masked out of the attacker set.  Which piece moves does not matter for that, only whether it is the king or
+// a pawn taking en passant (two bit tests instead of the six-way scans and key updates of a real make-move), so all
+// lanes of a warp run the same few instructions whatever their move is.
+KB_HD bool move_is_legal(const Pos& p, u16 mv) {
+    const int src = (mv >> 6) & 63, dst = mv & 63;
+    const int us = p.ctm;
+    const u64 sb = bit(src), db = bit(dst);
+    const u64 occ = occ_all(p);
+    const u64 own = us == WHITE ? p.white : (occ ^ p.white);
+    u64 enemy = (occ ^ own) & ~db;       // a captured piece no longer attacks
+    u64 occ2 = (occ & ~sb) | db;
+    const bool is_king = (p.pc[KING] & sb) != 0;
+    if ((p.pc[PAWN] & sb) && dst == p.ep) {  // en passant: the victim stands beside the source (p.ep == 0xFF matches no square)
+        const u64 vb = bit((src & 56) | (dst & 7));
+        occ2 &= ~vb;
+        enemy &= ~vb;
+    }
+    int ks = lsb(p.pc[KING] & own);
+    if (is_king) {
+        const int df = (dst & 7) - (src & 7);
+        if (df > 1 || df < -1) {  // castling: the rook jumps over the king
+            const int base = us == WHITE ? 0 : 56;
+            const bool kside = dst > src;
+            occ2 = (occ2 & ~bit(base + (kside ? 7 : 0))) | bit(base + (kside ? 5 : 3));
+        }
+        ks = dst;
+    }
+    const u64 att = (pawn_attacks(us, ks) & p.pc[PAWN]) | (knight_attacks(ks) & p.pc[KNIGHT]) |
+                    (bishop_attacks(ks, occ2) & (p.pc[BISHOP] | p.pc[QUEEN])) | (rook_attacks(ks, occ2) & (p.pc[ROOK] | p.pc[QUEEN])) |
+                    (king_attacks(ks) & p.pc[KING]);
+    return (att & enemy) == 0;
+}
+
 // position.c:316-319: is the side to move in check
 KB_HD u8 in_check(const Pos& p) {
     const u64 occ = occ_all(p);
@@ -520,9 +556,8 @@ KB_HDN int legal_actions_scalar(const Pos& p, u16* actions, u16* moves_out = nul
         }
     }
     int k = 0;
-    Pos tmp;
     for (int i = 0; i < n; ++i)
-        if (make_move<false>(p, l.mv[i], tmp)) {
+        if (move_is_legal(p, l.mv[i])) {
             if (moves_out) moves_out[k] = l.mv[i];
             actions[k++] = (u16)encode_action(p, l.mv[i]);
         }

@@ -17,6 +17,20 @@ int hc_legal_actions(const void* pos80, int* out) {
     for (int i = 0; i < n; ++i) out[i] = a[i];
     return n;
 }
+// every pseudo-legal move of the position: move_is_legal must give make_move<false>'s verdict; returns the number of
+// disagreements and the number of moves tested
+int hc_legality_diff(const void* pos80, int* tested) {
+    const Pos& p = *(const Pos*)pos80;
+    MoveList l;
+    gen_pseudo_legal(p, l);
+    int bad = 0;
+    for (int i = 0; i < l.n && i < MAX_MOVES; ++i) {
+        Pos tmp;
+        if (make_move<false>(p, l.mv[i], tmp) != move_is_legal(p, l.mv[i])) ++bad;
+    }
+    *tested = l.n < MAX_MOVES ? l.n : MAX_MOVES;
+    return bad;
+}
 int hc_push(void* pos80, int action) {
     Pos cur = *(Pos*)pos80, nx;
     bool legal = make_move<true>(cur, decode_action(cur, action), nx);

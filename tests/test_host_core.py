@@ -32,6 +32,27 @@ def vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def test_fast_legality_equals_make_move(hc):
+    """move_is_legal (attack lookup under the post-move occupancy, csrc/chess.cuh) == the verdict of a real make-move on
+    every pseudo-legal move of positions from seeded random games: checks, pins, en passant (incl. the discovered-check
+    cases), castling, promotions and king steps next to sliders all occur."""
+    rng = random.Random(11)
+    tested = bad = 0
+    n = C.c_int()
+    for g in range(220):
+        pos = np.zeros(80, np.uint8)
+        hc.hc_start(vp(pos))
+        for ply in range(160):
+            bad += hc.hc_legality_diff(vp(pos), C.byref(n))
+            tested += n.value
+            buf = np.zeros(128, np.int32)
+            k = hc.hc_legal_actions(vp(pos), buf.ctypes.data_as(C.POINTER(C.c_int)))
+            if k == 0:
+                break
+            hc.hc_push(vp(pos), int(buf[rng.randrange(k)]))
+    assert tested > 400000 and bad == 0, (tested, bad)
+
+
 def test_device_core_matches_oracle(hc):
     rng = random.Random(5)
     npos = 0
