@@ -58,7 +58,9 @@ static_assert(sizeof(Pos) == 80, "kb_position layout");
 constexpr int ZK_CASTLE = 768, ZK_EP = 784, ZK_BTM = 792, ZK_COUNT = 793;
 #if defined(__CUDACC__)
 // defined here: exactly one translation unit (tree.cu) includes this header under nvcc
-static __device__ u64 d_zobrist[ZK_COUNT];
+// __constant__: the tree descent reads it with warp-uniform indices (a broadcast from the constant cache instead of a
+// global load in the middle of every key update); 793 keys = 6.3 KB
+static __constant__ u64 d_zobrist[ZK_COUNT];
 #define KB_ZK(i) (kb::d_zobrist[(i)])
 #else
 extern u64 h_zobrist[ZK_COUNT];
