@@ -784,6 +784,7 @@ struct FusedParams {
     unsigned sync_target;
     float bv;
     int n_bias, items, boards, n_layers, tower_layers;
+    int mma_ws;  // 1: N = 64 / 128 layers issue tcgen05.mma.ws with the weight block held in a collector buffer (KB_TOWER_WS)
     FusedLayer layer[16];
 };
 #ifndef KB_TOWER_PIPE_DEFAULT
@@ -925,6 +926,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                 const uint32_t a_src = region_s + L.src_off;
                 const int nsub = L.n / L.n_sub, ksteps = L.ksteps, ntaps = L.ntaps, n = L.n;
                 const uint32_t idesc = L.idesc;
+                const bool ws = P.mma_ws != 0 && (L.n_sub == 64 || L.n_sub == 128);  // (the .ws form takes N = 64, 128, 256 only)
                 const uint32_t a_hi = ptx::sw128_hi(TALL_PITCH * LINE_BYTES), b_hi = ptx::sw128_hi(1024);
                 // weight blocks arrive in the order (sub-block, slab, tap)
                 for (int sub = 0; sub < nsub; ++sub)
@@ -939,14 +941,36 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                             const uint32_t b_lo0 = ptx::sw128_lo(ring_s + stage * FZ_STAGE);
                             if (ptx::elect_one()) {
                                 uint32_t first = (ks | tap) == 0 ? 0u : 1u;
-                                for (int kk = 0; kk < ksteps; ++kk) {
-                                    const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
-#pragma unroll
-                                    for (int mt = 0; mt < 4; ++mt) {
-                                        const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * (16 * TALL_PITCH * LINE_BYTES / 16), a_hi);
-                                        ptx::mma_bf16(d_base + mt * n, adesc, bdesc, idesc, first);
+                                constexpr uint32_t MT_STEP = 16 * TALL_PITCH * LINE_BYTES / 16;
+                                if (ws) {
+                                    // the weight block of a K step stays in a collector buffer for its four M tiles (buffers
+                                    // alternate so the next fill does not wait for the last use)
+                                    for (int kk = 0; kk < ksteps; ++kk) {
+                                        const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
+                                        const uint32_t a0 = a_tap + kk * 2;
+                                        if (kk & 1) {
+                                            ptx::mma_bf16_ws<1, 0>(d_base, ptx::desc_pack(a0, a_hi), bdesc, idesc, first);
+                                            ptx::mma_bf16_ws<1, 1>(d_base + n, ptx::desc_pack(a0 + MT_STEP, a_hi), bdesc, idesc, first);
+                                            ptx::mma_bf16_ws<1, 1>(d_base + 2 * n, ptx::desc_pack(a0 + 2 * MT_STEP, a_hi), bdesc, idesc, first);
+                                            ptx::mma_bf16_ws<1, 2>(d_base + 3 * n, ptx::desc_pack(a0 + 3 * MT_STEP, a_hi), bdesc, idesc, first);
+                                        } else {
+                                            ptx::mma_bf16_ws<0, 0>(d_base, ptx::desc_pack(a0, a_hi), bdesc, idesc, first);
+                                            ptx::mma_bf16_ws<0, 1>(d_base + n, ptx::desc_pack(a0 + MT_STEP, a_hi), bdesc, idesc, first);
+                                            ptx::mma_bf16_ws<0, 1>(d_base + 2 * n, ptx::desc_pack(a0 + 2 * MT_STEP, a_hi), bdesc, idesc, first);
+                                            ptx::mma_bf16_ws<0, 2>(d_base + 3 * n, ptx::desc_pack(a0 + 3 * MT_STEP, a_hi), bdesc, idesc, first);
+                                        }
+                                        first = 1u;
                                     }
-                                    first = 1u;
+                                } else {
+                                    for (int kk = 0; kk < ksteps; ++kk) {
+                                        const uint64_t bdesc = ptx::desc_pack(b_lo0 + kk * 2, b_hi);
+#pragma unroll
+                                        for (int mt = 0; mt < 4; ++mt) {
+                                            const uint64_t adesc = ptx::desc_pack(a_tap + kk * 2 + mt * MT_STEP, a_hi);
+                                            ptx::mma_bf16(d_base + mt * n, adesc, bdesc, idesc, first);
+                                        }
+                                        first = 1u;
+                                    }
                                 }
                                 ptx::mma_commit(b_empty(stage));
                             }
@@ -1946,6 +1970,10 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         std::vector<float> allb;
         FusedParams& fp = net->fp;
         memset(&fp, 0, sizeof(fp));
+        {   // (read per load like KB_TOWER_PIPE, so a test can compare both issue forms)
+            const char* w = getenv("KB_TOWER_WS");
+            fp.mma_ws = w ? atoi(w) : 1;
+        }
         const int XOFF = 0, YOFF = SLAB_BYTES;
         fp.n_layers = (int)net->layers.size();
         fp.tower_layers = 1 + 2 * R;

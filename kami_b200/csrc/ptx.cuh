@@ -110,6 +110,27 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Weight-stationary form: B stays in collector buffer BUF across the MMAs of one K step that share it (OP 0 = fill on the
+// first M tile, 1 = use, 2 = last use).  Same accumulator layout and bit-identical results as mma_bf16 for M = 128
+// (tools/mma_ws_probe.cu on a B200: 50.8 -> 44.2 cycles per 128x64x16 MMA, four M tiles per weight block); N must be
+// 64, 128 or 256.
+template <int BUF, int OP>
+__device__ __forceinline__ void mma_bf16_ws(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+#define KB_WS_MMA(SUFFIX)                                                                                                                      \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.ws.cta_group::1.kind::f16.collector::" SUFFIX " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), \
+                 "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)                                                                            \
+                 : "memory")
+    if constexpr (BUF == 0) {
+        if constexpr (OP == 0) KB_WS_MMA("b0::fill");
+        else if constexpr (OP == 1) KB_WS_MMA("b0::use");
+        else KB_WS_MMA("b0::lastuse");
+    } else {
+        if constexpr (OP == 0) KB_WS_MMA("b1::fill");
+        else if constexpr (OP == 1) KB_WS_MMA("b1::use");
+        else KB_WS_MMA("b1::lastuse");
+    }
+#undef KB_WS_MMA
+}
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -577,6 +577,18 @@ def test_tower_variants_agree_bit_for_bit(kb):
     assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
     op, ov = NO.forward(params, obs[:64])
     assert np.abs(nets["1"].forward_full(obs[:64])[1] - ov).max() <= 1e-2
+    # the weight-stationary issue form (tcgen05.mma.ws, weight block held in a collector buffer; the default) against the
+    # plain one: same products, same accumulation order per accumulator
+    os.environ["KB_TOWER_WS"] = "0"
+    try:
+        plain = kb.NN(64, 2)
+        plain.load_blob(blob)
+    finally:
+        del os.environ["KB_TOWER_WS"]
+    for batch in (obs[:7], obs, big):
+        p0, v0 = nets["0"].forward_full(batch)
+        p2, v2 = plain.forward_full(batch)
+        assert np.array_equal(p0, p2) and np.array_equal(v0, v2)
     kw = dict(noise_weight=0.05, selfplay_nodes=16, seed=8, alpha_initial=1.0, alpha_final=1.0, **H.DEF_YML)
     a = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
     b = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
