@@ -785,6 +785,7 @@ struct FusedParams {
     float bv;
     int n_bias, items, boards, n_layers, tower_layers;
     int mma_ws;  // 1: N = 64 / 128 layers issue tcgen05.mma.ws with the weight block held in a collector buffer (KB_TOWER_WS)
+    int wait_group;  // weight blocks the MMA warp waits for at a time, 1..FZ_NSTAGE (KB_TOWER_WAIT_GROUP, default 3)
     FusedLayer layer[16];
 };
 #ifndef KB_TOWER_PIPE_DEFAULT
@@ -799,6 +800,126 @@ constexpr int FZ_SMEM = FZ_HDR + FZ_REGION + FZ_NSTAGE * FZ_STAGE;
 // the epilogue phases, which alternate with the MMA phases (layer l + 1 needs all of layer l), halve.
 static_assert(FZ_SMEM <= 232448, "fused tower shared memory budget");
 static_assert(FZ_STAGE % 1024 == 0 && FZ_HDR % 1024 == 0, "swizzled operands need 1024-byte aligned bases");
+
+// Straight-line issue of one 3x3 layer with 64 output channels (nine weight blocks of KSTEPS K steps, four M tiles),
+// by ONE lane.  The tensor pipe's issue queue is short: anything but uniform-register arithmetic between two MMAs shows
+// as idle tensor cycles (tools/mma_ws_probe.cu, cycles per 128x64x16 MMA: 43.8 issued straight; 51.0 with an election +
+// __syncwarp per 16; 55.4 with a wait per 16 -- an mbarrier try_wait that succeeds at once, even a plain shared-memory
+// load).  So every descriptor of the layer is a compile-time offset from values computed before the first MMA, and the
+// lane looks at the weight ring three times per layer instead of nine: before block 0 (blocks 0..4: the whole ring, loaded
+// during the previous epilogue), before block 5 (5, 6) and before block 7 (7, 8) -- block j + 5 is requested when block
+// j's MMAs retire, about 1.3 k cycles before it is due here.
+template <int KSTEPS, bool WS>
+__device__ __forceinline__ void tower_issue_3x3_n64(uint32_t a_lo0, uint32_t a_hi, uint32_t b_hi, uint32_t d_base, uint32_t idesc, uint32_t ring_lo,
+                                                    uint32_t bar_full0, uint32_t bar_empty0, int stage, int phase, uint32_t bar_t_full) {
+    constexpr uint32_t MT_STEP = 16 * TALL_PITCH * LINE_BYTES / 16;
+    constexpr int N = 64;
+    static_assert(FZ_NSTAGE == 5, "wait schedule below assumes a 5-stage ring");
+    uint32_t b_lo[9], full[9], empty[9], par[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const int sj = stage + j;
+        const int wrap = sj >= 2 * FZ_NSTAGE ? 2 : sj >= FZ_NSTAGE ? 1 : 0;  // (stage <= 4, j <= 8: up to two laps)
+        const int sg = sj - wrap * FZ_NSTAGE;
+        b_lo[j] = ring_lo + (uint32_t)sg * (FZ_STAGE / 16);
+        full[j] = bar_full0 + 8u * sg;
+        empty[j] = bar_empty0 + 8u * sg;
+        par[j] = (uint32_t)(phase ^ (wrap & 1));
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        if (tap == 0) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) ptx::mbar_wait(full[j], par[j]);
+        } else if (tap == 5) {
+            ptx::mbar_wait(full[5], par[5]);
+            ptx::mbar_wait(full[6], par[6]);
+        } else if (tap == 7) {
+            ptx::mbar_wait(full[7], par[7]);
+            ptx::mbar_wait(full[8], par[8]);
+        }
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const uint32_t a_tap = a_lo0 + (uint32_t)((dy * TALL_PITCH + dx + 1) * (LINE_BYTES / 16));
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+            const uint64_t bdesc = ptx::desc_pack(b_lo[tap] + kk * 2, b_hi);
+            const uint32_t a0 = a_tap + kk * 2;
+            const uint32_t acc = (tap | kk) != 0 ? 1u : 0u;
+            if constexpr (WS) {
+                // the weight block of a K step stays in a collector buffer for its four M tiles (buffers alternate so the
+                // next fill does not wait for the last use)
+                if (kk & 1) {
+                    ptx::mma_bf16_ws<1, 0>(d_base, ptx::desc_pack(a0, a_hi), bdesc, idesc, acc);
+                    ptx::mma_bf16_ws<1, 1>(d_base + N, ptx::desc_pack(a0 + MT_STEP, a_hi), bdesc, idesc, acc);
+                    ptx::mma_bf16_ws<1, 1>(d_base + 2 * N, ptx::desc_pack(a0 + 2 * MT_STEP, a_hi), bdesc, idesc, acc);
+                    ptx::mma_bf16_ws<1, 2>(d_base + 3 * N, ptx::desc_pack(a0 + 3 * MT_STEP, a_hi), bdesc, idesc, acc);
+                } else {
+                    ptx::mma_bf16_ws<0, 0>(d_base, ptx::desc_pack(a0, a_hi), bdesc, idesc, acc);
+                    ptx::mma_bf16_ws<0, 1>(d_base + N, ptx::desc_pack(a0 + MT_STEP, a_hi), bdesc, idesc, acc);
+                    ptx::mma_bf16_ws<0, 1>(d_base + 2 * N, ptx::desc_pack(a0 + 2 * MT_STEP, a_hi), bdesc, idesc, acc);
+                    ptx::mma_bf16_ws<0, 2>(d_base + 3 * N, ptx::desc_pack(a0 + 3 * MT_STEP, a_hi), bdesc, idesc, acc);
+                }
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) ptx::mma_bf16(d_base + mt * N, ptx::desc_pack(a0 + mt * MT_STEP, a_hi), bdesc, idesc, acc);
+            }
+        }
+        ptx::mma_commit(empty[tap]);
+    }
+    ptx::mma_commit(bar_t_full);
+}
+
+// The same for the 1x1 head layers: NSUB x SLABS weight blocks (sub-block major), all waited for up front (they were
+// loaded during the previous epilogue), 64-channel K slabs.
+template <int NSUB, int SLABS, int N_SUB, bool WS>
+__device__ __forceinline__ void tower_issue_1x1(uint32_t a_lo0, uint32_t a_hi, uint32_t b_hi, uint32_t d_base, uint32_t idesc, uint32_t ring_lo,
+                                                uint32_t bar_full0, uint32_t bar_empty0, int stage, int phase, uint32_t bar_t_full) {
+    constexpr uint32_t MT_STEP = 16 * TALL_PITCH * LINE_BYTES / 16;
+    constexpr int NBLK = NSUB * SLABS, N = NSUB * N_SUB;
+    static_assert(NBLK <= FZ_NSTAGE, "all blocks of the layer must fit the ring");
+    uint32_t b_lo[NBLK], empty[NBLK];
+#pragma unroll
+    for (int j = 0; j < NBLK; ++j) {
+        const int sj = stage + j;
+        const int wrap = sj >= FZ_NSTAGE ? 1 : 0;
+        const int sg = sj - wrap * FZ_NSTAGE;
+        b_lo[j] = ring_lo + (uint32_t)sg * (FZ_STAGE / 16);
+        empty[j] = bar_empty0 + 8u * sg;
+        ptx::mbar_wait(bar_full0 + 8u * sg, (uint32_t)(phase ^ wrap));
+    }
+#pragma unroll
+    for (int sub = 0; sub < NSUB; ++sub)
+#pragma unroll
+        for (int ks = 0; ks < SLABS; ++ks) {
+            const int j = sub * SLABS + ks;
+            const uint32_t a_tap = a_lo0 + (uint32_t)ks * (SLAB_BYTES / 16) + (uint32_t)(LINE_BYTES / 16);  // centre tap: one pixel in
+            const uint32_t d = d_base + sub * N_SUB;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t bdesc = ptx::desc_pack(b_lo[j] + kk * 2, b_hi);
+                const uint32_t a0 = a_tap + kk * 2;
+                const uint32_t acc = (ks | kk) != 0 ? 1u : 0u;
+                if constexpr (WS) {
+                    if (kk & 1) {
+                        ptx::mma_bf16_ws<1, 0>(d, ptx::desc_pack(a0, a_hi), bdesc, idesc, acc);
+                        ptx::mma_bf16_ws<1, 1>(d + N, ptx::desc_pack(a0 + MT_STEP, a_hi), bdesc, idesc, acc);
+                        ptx::mma_bf16_ws<1, 1>(d + 2 * N, ptx::desc_pack(a0 + 2 * MT_STEP, a_hi), bdesc, idesc, acc);
+                        ptx::mma_bf16_ws<1, 2>(d + 3 * N, ptx::desc_pack(a0 + 3 * MT_STEP, a_hi), bdesc, idesc, acc);
+                    } else {
+                        ptx::mma_bf16_ws<0, 0>(d, ptx::desc_pack(a0, a_hi), bdesc, idesc, acc);
+                        ptx::mma_bf16_ws<0, 1>(d + N, ptx::desc_pack(a0 + MT_STEP, a_hi), bdesc, idesc, acc);
+                        ptx::mma_bf16_ws<0, 1>(d + 2 * N, ptx::desc_pack(a0 + 2 * MT_STEP, a_hi), bdesc, idesc, acc);
+                        ptx::mma_bf16_ws<0, 2>(d + 3 * N, ptx::desc_pack(a0 + 3 * MT_STEP, a_hi), bdesc, idesc, acc);
+                    }
+                } else {
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) ptx::mma_bf16(d + mt * N, ptx::desc_pack(a0 + mt * MT_STEP, a_hi), bdesc, idesc, acc);
+                }
+            }
+            ptx::mma_commit(empty[j]);
+        }
+    ptx::mma_commit(bar_t_full);
+}
 
 template <int N>
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory"); }
@@ -913,6 +1034,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
         // ===== MMA issuer (converged warp, one elected lane issues) =====
         int stage = 0, sphase = 0;
         uint32_t act_phase = 0;
+        const int wgroup = P.wait_group;
         if (!P.sync) pdl_wait();  // (this role touches nothing of the producing kernel: its inputs arrive through p_full)
         for (int ii = 0; ii < my_items; ++ii) {
             for (int l = 0; l < P.n_layers; ++l) {
@@ -923,23 +1045,67 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                     act_phase ^= 1;
                 }
                 ptx::tc_fence_after();
+                const bool mstamp = P.ts != nullptr && blockIdx.x == 0 && ii == 0;
                 const uint32_t a_src = region_s + L.src_off;
                 const int nsub = L.n / L.n_sub, ksteps = L.ksteps, ntaps = L.ntaps, n = L.n;
                 const uint32_t idesc = L.idesc;
                 const bool ws = P.mma_ws != 0 && (L.n_sub == 64 || L.n_sub == 128);  // (the .ws form takes N = 64, 128, 256 only)
                 const uint32_t a_hi = ptx::sw128_hi(TALL_PITCH * LINE_BYTES), b_hi = ptx::sw128_hi(1024);
-                // weight blocks arrive in the order (sub-block, slab, tap)
-                for (int sub = 0; sub < nsub; ++sub)
-                    for (int ks = 0; ks < L.slabs_in; ++ks) {
-                        const uint32_t a_lo0 = ptx::sw128_lo(a_src + ks * SLAB_BYTES);
-                        const uint32_t d_base = tmem_base + sub * L.n_sub;
-                        int dy = ntaps == 9 ? -1 : 0, dx = ntaps == 9 ? -1 : 0;
-                        for (int tap = 0; tap < ntaps; ++tap) {
-                            const uint32_t a_tap = a_lo0 + (uint32_t)((dy * TALL_PITCH + dx + 1) * (LINE_BYTES / 16));
-                            ptx::mbar_wait(b_full(stage), sphase);
-                            ptx::tc_fence_after();
-                            const uint32_t b_lo0 = ptx::sw128_lo(ring_s + stage * FZ_STAGE);
-                            if (ptx::elect_one()) {
+                const int nblocks = nsub * L.slabs_in * ntaps;
+                // One election per layer: the elected lane waits for weight blocks, issues and commits on its own.  The
+                // tensor pipe's issue queue is short and anything but uniform-register arithmetic between two MMAs shows
+                // as idle tensor cycles (tools/mma_ws_probe.cu, cycles per 128x64x16 MMA: 43.8 issued straight; 51.0 with
+                // an election + __syncwarp per 16; 55.4 with a wait per 16 -- an mbarrier try_wait that succeeds at once,
+                // even a plain shared-memory load): so the lane also looks at the ring only every `wgroup` blocks and
+                // then waits for that many stages at once.  Weight blocks arrive in the order (sub-block, slab, tap).
+                const bool straight = ntaps == 9 && nsub == 1 && L.slabs_in == 1 && L.n_sub == 64 && (ksteps == 4 || ksteps == 2) && P.wait_group != 1;
+                const bool head_a = ntaps == 1 && nsub == 2 && L.slabs_in == 1 && L.n_sub == 64 && ksteps == 4 && P.wait_group != 1;  // policyconv
+                const bool head_b = ntaps == 1 && nsub == 1 && L.slabs_in == 2 && L.n_sub == 80 && ksteps == 4 && P.wait_group != 1;  // policyconv2
+                if (head_a || head_b) {
+                    if (ptx::elect_one()) {
+                        const long long m_t0 = mstamp ? clock64() : 0;
+                        const uint32_t a_lo0 = ptx::sw128_lo(a_src), ring_lo = ptx::sw128_lo(ring_s);
+                        if (head_b) tower_issue_1x1<1, 2, 80, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                        else if (ws) tower_issue_1x1<2, 1, 64, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                        else tower_issue_1x1<2, 1, 64, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                        if (mstamp && l < 16) P.ts[65 + 2 * l] = clock64() - m_t0;
+                    }
+                } else if (straight) {
+                    if (ptx::elect_one()) {
+                        const long long m_t0 = mstamp ? clock64() : 0;
+                        const uint32_t a_lo0 = ptx::sw128_lo(a_src), ring_lo = ptx::sw128_lo(ring_s);
+                        if (ksteps == 4) {
+                            if (ws) tower_issue_3x3_n64<4, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                            else tower_issue_3x3_n64<4, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                        } else {
+                            if (ws) tower_issue_3x3_n64<2, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                            else tower_issue_3x3_n64<2, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                        }
+                        if (mstamp && l < 16) P.ts[65 + 2 * l] = clock64() - m_t0;
+                    }
+                } else if (ptx::elect_one()) {
+                    const long long m_t0 = mstamp ? clock64() : 0;
+                    long long m_wait = 0;
+                    int st = stage, ph = sphase, blocks_left = nblocks, in_group = 0;
+                    for (int sub = 0; sub < nsub; ++sub)
+                        for (int ks = 0; ks < L.slabs_in; ++ks) {
+                            const uint32_t a_lo0 = ptx::sw128_lo(a_src + ks * SLAB_BYTES);
+                            const uint32_t d_base = tmem_base + sub * L.n_sub;
+                            int dy = ntaps == 9 ? -1 : 0, dx = ntaps == 9 ? -1 : 0;
+                            for (int tap = 0; tap < ntaps; ++tap) {
+                                const uint32_t a_tap = a_lo0 + (uint32_t)((dy * TALL_PITCH + dx + 1) * (LINE_BYTES / 16));
+                                if (in_group == 0) {
+                                    const long long m_c0 = mstamp ? clock64() : 0;
+                                    in_group = blocks_left < wgroup ? blocks_left : wgroup;
+                                    for (int g = 0; g < in_group; ++g) {
+                                        const int sg = st + g;
+                                        ptx::mbar_wait(b_full(sg < FZ_NSTAGE ? sg : sg - FZ_NSTAGE), sg < FZ_NSTAGE ? ph : ph ^ 1);
+                                    }
+                                    if (mstamp) m_wait += clock64() - m_c0;
+                                }
+                                --in_group;
+                                --blocks_left;
+                                const uint32_t b_lo0 = ptx::sw128_lo(ring_s + st * FZ_STAGE);
                                 uint32_t first = (ks | tap) == 0 ? 0u : 1u;
                                 constexpr uint32_t MT_STEP = 16 * TALL_PITCH * LINE_BYTES / 16;
                                 if (ws) {
@@ -972,21 +1138,29 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                                         first = 1u;
                                     }
                                 }
-                                ptx::mma_commit(b_empty(stage));
-                            }
-                            __syncwarp();
-                            if (++stage == FZ_NSTAGE) {
-                                stage = 0;
-                                sphase ^= 1;
-                            }
-                            if (++dx > 1) {
-                                dx = -1;
-                                ++dy;
+                                ptx::mma_commit(b_empty(st));
+                                if (++st == FZ_NSTAGE) {
+                                    st = 0;
+                                    ph ^= 1;
+                                }
+                                if (++dx > 1) {
+                                    dx = -1;
+                                    ++dy;
+                                }
                             }
                         }
+                    ptx::mma_commit(t_full);
+                    if (mstamp && l < 16) {  // (profiling hook: weight waits and issue span of the issuing lane per layer)
+                        P.ts[64 + 2 * l] = m_wait;
+                        P.ts[65 + 2 * l] = clock64() - m_t0;
                     }
-                if (ptx::elect_one()) ptx::mma_commit(t_full);
+                }
                 __syncwarp();
+                {   // every lane keeps the ring position
+                    const int adv = stage + nblocks;
+                    sphase ^= (adv / FZ_NSTAGE) & 1;
+                    stage = adv % FZ_NSTAGE;
+                }
             }
             if (ii + 1 == my_items) pdl_launch_dependents();
             // the last layer's epilogue also signals act_ready (TMEM drained) -- consume it
@@ -1973,6 +2147,10 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         {   // (read per load like KB_TOWER_PIPE, so a test can compare both issue forms)
             const char* w = getenv("KB_TOWER_WS");
             fp.mma_ws = w ? atoi(w) : 1;
+            const char* g = getenv("KB_TOWER_WAIT_GROUP");
+            fp.wait_group = g ? atoi(g) : 3;
+            if (fp.wait_group < 1) fp.wait_group = 1;
+            if (fp.wait_group > FZ_NSTAGE) fp.wait_group = FZ_NSTAGE;
         }
         const int XOFF = 0, YOFF = SLAB_BYTES;
         fp.n_layers = (int)net->layers.size();
@@ -2222,7 +2400,11 @@ int kb_net_debug_timestamps(kb_net* net, int enable, long long* out, int cap, in
         KB_CUDA(cudaStreamSynchronize(main_stream()));
         KB_CUDA(cudaMemcpy(h, net->ts_dev, sizeof(h), cudaMemcpyDeviceToHost));
         int n = 0;
-        while (n < (kb::g_conv_ts ? 128 : 60) && n < cap && (h[n] || kb::g_conv_ts)) { out[n] = h[n]; ++n; }
+        if (cap >= 128) {  // raw: stamps in [0, 60), the MMA warp's per-layer {weight wait, issue span} pairs from 64
+            for (; n < 128; ++n) out[n] = h[n];
+        } else {
+            while (n < (kb::g_conv_ts ? 128 : 60) && n < cap && (h[n] || kb::g_conv_ts)) { out[n] = h[n]; ++n; }
+        }
         if (count) *count = n;
     }
     if (!enable && net->ts_dev) {
