@@ -784,6 +784,7 @@ struct FusedParams {
     unsigned sync_target;
     float bv;
     int n_bias, items, boards, n_layers, tower_layers;
+    int wv_off;  // the value conv's 64 folded weights sit behind the biases in shared memory (float offset, multiple of 4)
     int mma_ws;  // 1: N = 64 / 128 layers issue tcgen05.mma.ws with the weight block held in a collector buffer (KB_TOWER_WS)
     int wait_group;  // weight blocks the MMA warp waits for at a time, 1..FZ_NSTAGE (KB_TOWER_WAIT_GROUP, default 3)
     FusedLayer layer[16];
@@ -811,7 +812,8 @@ static_assert(FZ_STAGE % 1024 == 0 && FZ_HDR % 1024 == 0, "swizzled operands nee
 // j's MMAs retire, about 1.3 k cycles before it is due here.
 template <int KSTEPS, bool WS>
 __device__ __forceinline__ void tower_issue_3x3_n64(uint32_t a_lo0, uint32_t a_hi, uint32_t b_hi, uint32_t d_base, uint32_t idesc, uint32_t ring_lo,
-                                                    uint32_t bar_full0, uint32_t bar_empty0, int stage, int phase, uint32_t bar_t_full) {
+                                                    uint32_t bar_full0, uint32_t bar_empty0, int stage, int phase, uint32_t bar_t_full,
+                                                    uint32_t bar_in, uint32_t par_in) {
     constexpr uint32_t MT_STEP = 16 * TALL_PITCH * LINE_BYTES / 16;
     constexpr int N = 64;
     static_assert(FZ_NSTAGE == 5, "wait schedule below assumes a 5-stage ring");
@@ -831,6 +833,10 @@ __device__ __forceinline__ void tower_issue_3x3_n64(uint32_t a_lo0, uint32_t a_h
         if (tap == 0) {
 #pragma unroll
             for (int j = 0; j < 5; ++j) ptx::mbar_wait(full[j], par[j]);
+            // the layer's input last: the previous layer written to shared memory and its accumulators drained (or the
+            // planes landed) -- everything else this lane needs is already in registers when that happens
+            ptx::mbar_wait(bar_in, par_in);
+            ptx::tc_fence_after();
         } else if (tap == 5) {
             ptx::mbar_wait(full[5], par[5]);
             ptx::mbar_wait(full[6], par[6]);
@@ -873,7 +879,8 @@ __device__ __forceinline__ void tower_issue_3x3_n64(uint32_t a_lo0, uint32_t a_h
 // loaded during the previous epilogue), 64-channel K slabs.
 template <int NSUB, int SLABS, int N_SUB, bool WS>
 __device__ __forceinline__ void tower_issue_1x1(uint32_t a_lo0, uint32_t a_hi, uint32_t b_hi, uint32_t d_base, uint32_t idesc, uint32_t ring_lo,
-                                                uint32_t bar_full0, uint32_t bar_empty0, int stage, int phase, uint32_t bar_t_full) {
+                                                uint32_t bar_full0, uint32_t bar_empty0, int stage, int phase, uint32_t bar_t_full, uint32_t bar_in,
+                                                uint32_t par_in) {
     constexpr uint32_t MT_STEP = 16 * TALL_PITCH * LINE_BYTES / 16;
     constexpr int NBLK = NSUB * SLABS, N = NSUB * N_SUB;
     static_assert(NBLK <= FZ_NSTAGE, "all blocks of the layer must fit the ring");
@@ -887,6 +894,8 @@ __device__ __forceinline__ void tower_issue_1x1(uint32_t a_lo0, uint32_t a_hi, u
         empty[j] = bar_empty0 + 8u * sg;
         ptx::mbar_wait(bar_full0 + 8u * sg, (uint32_t)(phase ^ wrap));
     }
+    ptx::mbar_wait(bar_in, par_in);
+    ptx::tc_fence_after();
 #pragma unroll
     for (int sub = 0; sub < NSUB; ++sub)
 #pragma unroll
@@ -1039,12 +1048,9 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
         for (int ii = 0; ii < my_items; ++ii) {
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
-                if (l == 0) ptx::mbar_wait(p_full, ii & 1);
-                else {
-                    ptx::mbar_wait(act_ready, act_phase);  // previous layer written to smem, TMEM drained
-                    act_phase ^= 1;
-                }
-                ptx::tc_fence_after();
+                // input of the layer: the planes (layer 0), else the previous layer written to smem and TMEM drained
+                const uint32_t in_bar = l == 0 ? p_full : act_ready, in_par = l == 0 ? (uint32_t)(ii & 1) : act_phase;
+                if (l != 0) act_phase ^= 1;
                 const bool mstamp = P.ts != nullptr && blockIdx.x == 0 && ii == 0;
                 const uint32_t a_src = region_s + L.src_off;
                 const int nsub = L.n / L.n_sub, ksteps = L.ksteps, ntaps = L.ntaps, n = L.n;
@@ -1065,9 +1071,9 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                     if (ptx::elect_one()) {
                         const long long m_t0 = mstamp ? clock64() : 0;
                         const uint32_t a_lo0 = ptx::sw128_lo(a_src), ring_lo = ptx::sw128_lo(ring_s);
-                        if (head_b) tower_issue_1x1<1, 2, 80, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
-                        else if (ws) tower_issue_1x1<2, 1, 64, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
-                        else tower_issue_1x1<2, 1, 64, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                        if (head_b) tower_issue_1x1<1, 2, 80, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full, in_bar, in_par);
+                        else if (ws) tower_issue_1x1<2, 1, 64, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full, in_bar, in_par);
+                        else tower_issue_1x1<2, 1, 64, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full, in_bar, in_par);
                         if (mstamp && l < 16) P.ts[65 + 2 * l] = clock64() - m_t0;
                     }
                 } else if (straight) {
@@ -1075,15 +1081,17 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                         const long long m_t0 = mstamp ? clock64() : 0;
                         const uint32_t a_lo0 = ptx::sw128_lo(a_src), ring_lo = ptx::sw128_lo(ring_s);
                         if (ksteps == 4) {
-                            if (ws) tower_issue_3x3_n64<4, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
-                            else tower_issue_3x3_n64<4, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                            if (ws) tower_issue_3x3_n64<4, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full, in_bar, in_par);
+                            else tower_issue_3x3_n64<4, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full, in_bar, in_par);
                         } else {
-                            if (ws) tower_issue_3x3_n64<2, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
-                            else tower_issue_3x3_n64<2, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full);
+                            if (ws) tower_issue_3x3_n64<2, true>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full, in_bar, in_par);
+                            else tower_issue_3x3_n64<2, false>(a_lo0, a_hi, b_hi, tmem_base, idesc, ring_lo, b_full(0), b_empty(0), stage, sphase, t_full, in_bar, in_par);
                         }
                         if (mstamp && l < 16) P.ts[65 + 2 * l] = clock64() - m_t0;
                     }
                 } else if (ptx::elect_one()) {
+                    ptx::mbar_wait(in_bar, in_par);
+                    ptx::tc_fence_after();
                     const long long m_t0 = mstamp ? clock64() : 0;
                     long long m_wait = 0;
                     int st = stage, ph = sphase, blocks_left = nblocks, in_group = 0;
@@ -1263,7 +1271,6 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                 t_phase ^= 1;
                 ptx::tc_fence_after();
                 KB_STAMP();
-                if (l == P.tower_layers) epi_bar();  // every warp finished reading X for the value head
                 const int ncg = L.n / 16;
                 // The two warps of a lane quarter split the TILES (even / odd), not the columns: the same instruction count
                 // per warp, but half as many dependent TMEM-load -> convert -> store chains for the 64-column tower layers.
@@ -1343,25 +1350,34 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                 KB_STAMP();
                 if (l == P.tower_layers - 1) {
                     // ---- value conv 1x1 + ReLU on X (nn.cpp:83-86); the 64 -> 256 Linear + tanh runs on warps 2-3 ----
-                    epi_bar();  // X complete
+                    // Every thread takes the pixels it has just written itself (and is the only one to overwrite with the
+                    // policy head's output later): no barrier on either side.  The folded weights sit behind the biases
+                    // in shared memory.  fp32 fma chain in channel order from the folded bias.
                     if (ii > 0) named_bar_sync<FC_BAR>(3);  // vbuf consumed by the previous item's Linear
                     const uint4* X = reinterpret_cast<const uint4*>(region + P.layer[l].dst_off);
-                    for (int i = et; i < NB * 64; i += FZ_EPI_THREADS) {
-                        const int slot = i >> 6, pix = i & 63;
-                        const int px = tall_pixel(slot, pix);
+                    const float4* wv4 = reinterpret_cast<const float4*>(sbias + P.wv_off);
+#pragma unroll 1
+                    for (int mt = half; mt < 4; mt += PARTS) {
+                        const int r = 32 * q + lane;
+                        const int R = 16 * mt + (r >> 3), x = r & 7;
+                        const int slot = (R - 1) / 9, y = (R - 1) - slot * 9;
+                        if (!(R >= 1 && y < 8 && slot < NB)) continue;
+                        const int px = R * TALL_PITCH + 1 + x;
                         float acc = P.bv;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint4 a4 = X[chunk_u4(px, c)];
+                            const float4 wa = wv4[2 * c], wb = wv4[2 * c + 1];
                             const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&a4);
+                            const float wvv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float2 av = __bfloat1622float2(ab[k]);
-                                acc = fmaf(av.x, __ldg(P.wv + c * 8 + 2 * k), acc);
-                                acc = fmaf(av.y, __ldg(P.wv + c * 8 + 2 * k + 1), acc);
+                                acc = fmaf(av.x, wvv[2 * k], acc);
+                                acc = fmaf(av.y, wvv[2 * k + 1], acc);
                             }
                         }
-                        vbuf[i] = fmaxf(acc, 0.0f);
+                        vbuf[slot * 64 + y * 8 + x] = fmaxf(acc, 0.0f);
                     }
                     named_bar_arrive<FC_BAR>(2);  // vbuf ready for warps 2-3
                 }
@@ -2108,6 +2124,7 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
     }
     if ((r = conv_bn(128, F, 1, fs, 4, ntile, 128, 1, true))) return r;               // policyconv + pbatchnorm + relu
     if ((r = conv_bn(73, 128, 1, 2, 4, 80, 80, 0, false))) return r;                  // policyconv2 (logits)
+    std::vector<float> wv_host;  // (the fused tower also keeps the value conv's weights in shared memory)
     {   // value head
         const float* w = c.take(F);
         const float* b = c.take(1);
@@ -2127,6 +2144,7 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         KB_CUDA(cudaMemcpy(net->wv, wv.data(), F * 4, cudaMemcpyHostToDevice));
         KB_CUDA(cudaMemcpy(net->fct, fct.data(), 64 * 256 * 4, cudaMemcpyHostToDevice));
         KB_CUDA(cudaMemcpy(net->fcb, fb, 256 * 4, cudaMemcpyHostToDevice));
+        wv_host = wv;
     }
     // fused single-kernel path: 64 filters, biases fit the kernel's shared-memory table
     net->fused = false;
@@ -2187,8 +2205,10 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
             allw.insert(allw.end(), L.hw.begin(), L.hw.end());
             allb.insert(allb.end(), L.hbias.begin(), L.hbias.end());
         }
+        fp.wv_off = (int)allb.size();
+        allb.insert(allb.end(), wv_host.begin(), wv_host.end());
         fp.n_bias = (int)allb.size();
-        if (fp.n_bias <= 1340 && fp.n_layers <= 16) {
+        if (fp.n_bias <= 1340 && fp.n_layers <= 16 && fp.wv_off % 4 == 0) {
             KB_CUDA(cudaMalloc(&net->fused_w, allw.size() * 2));
             KB_CUDA(cudaMemcpy(net->fused_w, allw.data(), allw.size() * 2, cudaMemcpyHostToDevice));
             KB_CUDA(cudaMalloc(&net->fused_bias, allb.size() * 4));
