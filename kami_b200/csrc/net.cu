@@ -786,6 +786,10 @@ struct FusedParams {
     int n_bias, items, boards, n_layers, tower_layers;
     int wv_off;  // the value conv's 64 folded weights sit behind the biases in shared memory (float offset, multiple of 4)
     int mma_ws;  // 1: N = 64 / 128 layers issue tcgen05.mma.ws with the weight block held in a collector buffer (KB_TOWER_WS)
+    int blocks_before_logits, blocks_per_item;  // weight-ring position of policyconv2's two blocks inside an item
+    int gather;  // 1: in legal-move mode the logits of the legal moves are computed where they are needed, from the policy head's
+                 //    features and policyconv2's rows in the weight ring, instead of all 4 672 by MMA (KB_TOWER_GATHER=1; measured
+                 //    62.0 k vs 64.0 k cycles per item on young games, 69.9 vs 70.1 us per step on aged ones: off by default)
     int wait_group;  // weight blocks the MMA warp waits for at a time, 1..FZ_NSTAGE (KB_TOWER_WAIT_GROUP, default 3)
     FusedLayer layer[16];
 };
@@ -1028,6 +1032,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(b_full(stage), bytes);
                         ptx::bulk_g2s(ring_s + stage * FZ_STAGE, w, bytes, b_full(stage));
+                        if (P.ts && blockIdx.x == 0 && ii == 0 && l >= P.n_layers - 3) P.ts[96 + (l - (P.n_layers - 3)) * 9 + b] = clock64();  // (profiling hook)
                     }
                     __syncwarp();
                     w += bytes / 16;
@@ -1045,9 +1050,16 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
         uint32_t act_phase = 0;
         const int wgroup = P.wait_group;
         if (!P.sync) pdl_wait();  // (this role touches nothing of the producing kernel: its inputs arrive through p_full)
+        const bool gather = P.legal_act != nullptr && P.gather != 0;
         for (int ii = 0; ii < my_items; ++ii) {
             for (int l = 0; l < P.n_layers; ++l) {
                 const FusedLayer& L = P.layer[l];
+                if (gather && L.kind == 1) {  // the epilogue warps read policyconv2's rows straight from the ring: keep its position
+                    const int adv = stage + L.slabs_in * L.ntaps * (L.n / L.n_sub);
+                    sphase ^= (adv / FZ_NSTAGE) & 1;
+                    stage = adv % FZ_NSTAGE;
+                    continue;
+                }
                 // input of the layer: the planes (layer 0), else the previous layer written to smem and TMEM drained
                 const uint32_t in_bar = l == 0 ? p_full : act_ready, in_par = l == 0 ? (uint32_t)(ii & 1) : act_phase;
                 if (l != 0) act_phase ^= 1;
@@ -1265,8 +1277,21 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
             }
             if (ii == 0 && !P.sync) pdl_wait();
             KB_STAMP();
-            for (int l = 0; l < P.n_layers; ++l) {
+            const bool gather = P.legal_act != nullptr && P.gather != 0;
+            int g_n = 0;                       // gather head: move count and four actions per lane of board `e`'s list
+            uint2 g_act4 = make_uint2(0, 0);
+            for (int l = 0; l < P.n_layers - (gather ? 1 : 0); ++l) {
                 const FusedLayer& L = P.layer[l];
+                if (gather && l == P.tower_layers && !P.sync && e < NB) {
+                    // the gather head below needs the boards' move lists in shared memory: warp b requests board b's row
+                    // now (count + 128 actions, one coalesced read) and parks it after this layer's epilogue, which
+                    // hides the L2 latency.  (Rows hold 128 entries: reading past the count is harmless.)
+                    const int pboard = item * NB + e;
+                    if (pboard < P.boards) {
+                        g_n = *reinterpret_cast<const int*>(P.legal_n + (size_t)pboard * P.legal_stride);
+                        g_act4 = reinterpret_cast<const uint2*>(P.legal_act + (size_t)pboard * P.legal_stride)[lane];
+                    }
+                }
                 ptx::mbar_wait(t_full, t_phase);
                 t_phase ^= 1;
                 ptx::tc_fence_after();
@@ -1382,11 +1407,127 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) k_tower64(const __grid_const
                     named_bar_arrive<FC_BAR>(2);  // vbuf ready for warps 2-3
                 }
             }
+            auto pad_row = [&](int b) { return region + (size_t)(9 * b) * TALL_PITCH * LINE_BYTES; };  // 1280 bytes: [128] logits, count, [128] actions
+            if (gather) {
+                if (e < NB) {  // park board e's move list (see the gather head below)
+                    const int board = item * NB + e;
+                    if (P.sync && board < P.boards) {  // split select: the lists were not there earlier
+                        wait_input(1);
+                        g_n = *reinterpret_cast<const int*>(P.legal_n + (size_t)board * P.legal_stride);
+                        g_act4 = reinterpret_cast<const uint2*>(P.legal_act + (size_t)board * P.legal_stride)[lane];
+                    }
+                    if (board >= P.boards) g_n = 0;
+                    if (lane == 0) *reinterpret_cast<int*>(pad_row(e) + 512) = g_n;
+                    reinterpret_cast<uint2*>(pad_row(e) + 528)[lane] = g_act4;
+                }
+                const int s_abs = ii * P.blocks_per_item + P.blocks_before_logits;  // policyconv2's two blocks in the ring
+                ptx::mbar_wait(b_full(s_abs % FZ_NSTAGE), (uint32_t)((s_abs / FZ_NSTAGE) & 1));
+                ptx::mbar_wait(b_full((s_abs + 1) % FZ_NSTAGE), (uint32_t)(((s_abs + 1) / FZ_NSTAGE) & 1));
+            }
             // ---- softmax over the 4672 logits of each board (nn.cpp:80) ----
-            epi_bar();
+            epi_bar();  // (gather head: H complete, move lists parked)
             if (ii + 1 == my_items) pdl_launch_dependents();
             KB_STAMP();
-            if (P.legal_act) {
+            if (gather) {
+                // ---- policyconv2 + softmax numerators for the legal moves only (nn.cpp:76-80) ----
+                // A board has ~30 legal moves, so 30 of its 4 672 logits are ever read: instead of the 1x1 conv over all
+                // pixels (32 MMAs, then 73 fp32 stores per pixel, then a gather) every legal move takes its pixel's 128
+                // features from H and policyconv2's row from the weight ring and does the 128-term dot product itself.
+                // Work unit = eight moves of one board, four lanes per move (32 features each, two fma chains, xor-shuffle
+                // sum); the units of the item's seven boards are dealt round-robin to ALL epilogue warps -- one warp runs
+                // this at ~4.5 cycles per instruction (dependent integer / convert / fma chains), so what matters is how
+                // many warps share it.  Move lists and raw logits wait in pad lines of the X slab (the pad row above each
+                // board: never written by the policy head, zero-filled again before the next item).
+                const FusedLayer& L = P.layer[P.n_layers - 1];
+                const int s_abs = ii * P.blocks_per_item + P.blocks_before_logits;  // (policyconv2 = two K slabs = two blocks)
+                const int st0 = s_abs % FZ_NSTAGE, st1 = (s_abs + 1) % FZ_NSTAGE;
+                {
+                    int ub[NB + 1];  // unit prefix over the boards
+                    ub[0] = 0;
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) ub[b + 1] = ub[b] + ((*reinterpret_cast<const int*>(pad_row(b) + 512) + 7) >> 3);
+                    const int mslot = lane >> 2, kq = lane & 3;
+                    const uint4* hslab = reinterpret_cast<const uint4*>(region + (kq >> 1) * SLAB_BYTES);
+                    const uint4* wblk = reinterpret_cast<const uint4*>(smem + FZ_HDR + FZ_REGION + ((kq >> 1) ? st1 : st0) * FZ_STAGE);
+                    const int c0 = (kq & 1) * 4;  // first 16-byte chunk of this lane's 32 features inside the 128-byte line
+#pragma unroll 1
+                    for (int u = e; u < ub[NB]; u += EW) {
+                        int b = 0;
+#pragma unroll
+                        for (int k = 1; k < NB; ++k) b += u >= ub[k] ? 1 : 0;
+                        int ubase = 0;
+#pragma unroll
+                        for (int k = 1; k < NB; ++k) ubase = b == k ? ub[k] : ubase;
+                        const uint8_t* row = pad_row(b);
+                        const int n = *reinterpret_cast<const int*>(row + 512);
+                        const int i = (u - ubase) * 8 + mslot;
+                        float a0 = 0.0f, a1 = 0.0f;
+                        int c = 0;
+                        if (i < n) {
+                            const int act = reinterpret_cast<const uint16_t*>(row + 528)[i];
+                            const int sq = act / 73;
+                            c = act - sq * 73;
+                            const int px = tall_pixel(b, sq);
+                            const uint4* hrow = hslab + px * 8;
+                            const uint4* wrow = wblk + c * 8;
+                            uint4 h4[4], w4[4];
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) {
+                                h4[ch] = hrow[(c0 + ch) ^ (px & 7)];
+                                w4[ch] = wrow[(c0 + ch) ^ (c & 7)];
+                            }
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) {
+                                const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&h4[ch]);
+                                const __nv_bfloat162* wb = reinterpret_cast<const __nv_bfloat162*>(&w4[ch]);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 hv = __bfloat1622float2(hb[t]), wv2 = __bfloat1622float2(wb[t]);
+                                    a0 = fmaf(hv.x, wv2.x, a0);
+                                    a1 = fmaf(hv.y, wv2.y, a1);
+                                }
+                            }
+                        }
+                        float lg = a0 + a1;
+                        lg += __shfl_xor_sync(0xffffffffu, lg, 1);
+                        lg += __shfl_xor_sync(0xffffffffu, lg, 2);
+                        if (i < n && kq == 0) reinterpret_cast<float*>(const_cast<uint8_t*>(row))[i] = lg + sbias[L.bias_off + c];
+                    }
+                }
+                KB_STAMP();
+                epi_bar();  // every logit written; every read of the weight ring done
+                KB_STAMP();
+                if (et == 0) {
+                    ptx::mbar_arrive(b_empty(st0));
+                    ptx::mbar_arrive(b_empty(st1));
+                }
+                if (e < NB) {  // warp b: maximum over board b's logits, numerators out
+                    const int board = item * NB + e;
+                    const uint8_t* row = pad_row(e);
+                    const int n = *reinterpret_cast<const int*>(row + 512);
+                    const float* lgs = reinterpret_cast<const float*>(row);
+                    float l[4];
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int i = lane + 32 * r;
+                        l[r] = i < n ? lgs[i] : -INFINITY;
+                        m = fmaxf(m, l[r]);
+                    }
+                    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                    bool bad = false;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int i = lane + 32 * r;
+                        if (i < n) {
+                            const float o = __expf(l[r] - m);
+                            bad |= (o != o);
+                            P.prior[(size_t)board * 128 + i] = o;
+                        }
+                    }
+                    if (bad) atomicExch(P.nan_flag, 1);
+                }
+            } else if (P.legal_act) {
                 if (P.sync) wait_input(1);  // the move lists are the last thing the producing kernel writes
                 // ---- softmax numerators over the legal moves only: warp e gathers board e's logits ----
                 const float* lg = reinterpret_cast<const float*>(region);
@@ -2165,6 +2306,8 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
         {   // (read per load like KB_TOWER_PIPE, so a test can compare both issue forms)
             const char* w = getenv("KB_TOWER_WS");
             fp.mma_ws = w ? atoi(w) : 1;
+            const char* ge = getenv("KB_TOWER_GATHER");
+            fp.gather = ge ? atoi(ge) : 0;
             const char* g = getenv("KB_TOWER_WAIT_GROUP");
             fp.wait_group = g ? atoi(g) : 3;
             if (fp.wait_group < 1) fp.wait_group = 1;
@@ -2205,6 +2348,13 @@ int kb_net_load_blob(kb_net* net, const float* blob, size_t n_floats) {
             allw.insert(allw.end(), L.hw.begin(), L.hw.end());
             allb.insert(allb.end(), L.hbias.begin(), L.hbias.end());
         }
+        fp.blocks_per_item = fp.blocks_before_logits = 0;
+        for (int l = 0; l < fp.n_layers; ++l) {
+            const FusedLayer& f = fp.layer[l];
+            if (l == fp.n_layers - 1) fp.blocks_before_logits = fp.blocks_per_item;
+            fp.blocks_per_item += f.slabs_in * f.ntaps * (f.n / f.n_sub);
+        }
+        if (fp.blocks_per_item - fp.blocks_before_logits != 2) fp.gather = 0;  // (the gather head reads exactly two K slabs)
         fp.wv_off = (int)allb.size();
         allb.insert(allb.end(), wv_host.begin(), wv_host.end());
         fp.n_bias = (int)allb.size();

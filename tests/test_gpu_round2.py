@@ -589,13 +589,46 @@ def test_tower_variants_agree_bit_for_bit(kb):
         p0, v0 = nets["0"].forward_full(batch)
         p2, v2 = plain.forward_full(batch)
         assert np.array_equal(p0, p2) and np.array_equal(v0, v2)
+    # pool step (legal-move mode): the trees the two kernels build must be identical.  With KB_TOWER_GATHER=1 k_tower64
+    # computes the logits of the legal moves only, as fp32 dot products on the CUDA cores, instead of taking them from the
+    # policyconv2 MMA (measured alternative, off by default): compared further down
+    mma_logits = nets["0"]
+    os.environ["KB_TOWER_GATHER"] = "1"
+    try:
+        gathered = kb.NN(64, 2)
+        gathered.load_blob(blob)
+    finally:
+        del os.environ["KB_TOWER_GATHER"]
     kw = dict(noise_weight=0.05, selfplay_nodes=16, seed=8, alpha_initial=1.0, alpha_final=1.0, **H.DEF_YML)
     a = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
     b = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
-    a.step(nets["0"], 60)
+    a.step(mma_logits, 60)
     b.step(nets["1"], 60)
     for t in range(300):
         assert a.tree(t).digest() == b.tree(t).digest(), t
+    # the gathered logits against the MMA's: both pools walk the same pseudo-random lines (one move per tree and round,
+    # chosen by index from the root's move list); the priors of every new root's expansion (no noise) agree to fp32 rounding
+    kw = dict(noise_weight=0.0, selfplay_nodes=0, seed=8, **H.DEF_YML)
+    c = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
+    d = kb.TreePool(300, 1 << 13, _cfg(kb, **kw))
+    worst, seen = 0.0, 0
+    for ply in range(10):
+        c.step(gathered, 1)
+        d.step(mma_logits, 1)
+        for t in range(300):
+            ac, _, _, pc = c.tree(t).root_children()
+            ad, _, _, pd = d.tree(t).root_children()
+            assert np.array_equal(ac, ad), (ply, t)
+            if len(pc) == 0:
+                continue
+            worst = max(worst, float(np.abs(pc - pd).max() / pd.max()))
+            seen += 1
+            mv = int(ac[(t * 7 + ply * 13) % len(ac)])
+            c.tree(t).push(mv)
+            d.tree(t).push(mv)
+    assert seen > 2500
+    print("gathered vs MMA logits: worst relative prior difference %.2e" % worst)
+    assert worst <= 2e-5
 
 
 def test_split_select_keeps_every_trees_own_sequence(kb):
