@@ -170,8 +170,11 @@ int kb_pool_leaf_actions(kb_pool* p, int32_t* actions /*[n][128] host*/, int32_t
 int kb_pool_expand_compact(kb_pool* p, const float* prior /*[n][128] host*/, const float* value /*[n] host*/, int disable_bootstrap);
 /* the whole loop of selfplay.cpp:113-200: select -> encode -> tower+heads -> expand/backup, `iters` times */
 int kb_pool_step(kb_pool* p, kb_net* net, int iters);
-/* same, but every iteration's leaf planes round-trip through host memory like the reference
- * (H2D of obs + D2H of policy/value inside the call); used for the end-to-end bench figure */
+/* same, but every iteration's data goes through the caller's host arrays like the reference's batch / inf_policy /
+ * inf_value (selfplay.cpp:107-109): leaf observations out and back in (NN::infer's input), dense policy rows + values out,
+ * values back in.  MCTS::expand reads policy[action] for the legal moves only (mcts.h:273): with a pinned policy array
+ * (kb_host_alloc_pinned / kb_host_register) the expand kernels read those entries straight from it; a pageable one is
+ * copied back to the device in full.  Used for the end-to-end bench figure. */
 int kb_pool_step_hostio(kb_pool* p, kb_net* net, int iters, float* obs_host, float* policy_host, float* value_host);
 /* kb_pool_step_hostio serves the trees as `groups` independent pipelines, the analogue of the reference's
  * inference_threads (selfplay.cpp:25-31): each group has its own NN::infer batch (so Q1's value indexing is per

@@ -366,7 +366,7 @@ def test_step_groups_equal_independent_pools(kb):
             assert solo.tree(i).digest() == pool.tree(g * per + i).digest(), (g, i)
 
 
-@pytest.mark.parametrize("dense", [0, 1])
+@pytest.mark.parametrize("dense", [0, 1, 2])
 def test_hostio_forms_build_the_same_trees_as_the_resident_step(kb, dense):
     """The host-buffer loops (reference-shaped dense rows, and the compact 80-byte / [128]-prior form) against the
     resident grouped step with the same group count: identical trees, noise and temperature on."""
@@ -378,10 +378,24 @@ def test_hostio_forms_build_the_same_trees_as_the_resident_step(kb, dense):
     a = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
     b = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
     a.set_step_groups(G)
-    a.set_policy_mode(dense)
+    a.set_policy_mode(1 if dense else 0)
     b.set_hostio_groups(G)
     val = np.zeros(n, np.float32)
-    if dense:
+    if dense == 2:
+        # pinned caller buffers: the expand kernels then read the legal moves' policy entries straight from the caller's
+        # dense array over PCIe instead of copying all of it back to the device (kb_pool_step_hostio)
+        import ctypes as C
+
+        L, ptrs = kb.lib(), []
+
+        def pinned(shape):
+            p = C.c_void_p()
+            api._ck(L.kb_host_alloc_pinned(C.byref(p), int(np.prod(shape)) * 4))
+            ptrs.append(p)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(int(np.prod(shape)),)).reshape(shape)
+
+        obs, pol = pinned((n, H.OBSIZE)), pinned((n, H.PSIZE))
+    elif dense:
         obs, pol = np.zeros((n, H.OBSIZE), np.float32), np.zeros((n, H.PSIZE), np.float32)
     else:
         leaves, prior = np.zeros(n, api.POSITION_DTYPE), np.zeros((n, 128), np.float32)
@@ -398,6 +412,10 @@ def test_hostio_forms_build_the_same_trees_as_the_resident_step(kb, dense):
         assert np.allclose(pol.sum(1), 1.0, atol=1e-4) and np.abs(obs).max() > 0
     else:
         assert leaves["ply"].max() > 0 and prior.max() == 1.0
+    if dense == 2:
+        del obs, pol
+        for p in ptrs:
+            L.kb_host_free_pinned(p)
 
 
 def test_leaf_actions_and_compact_expand(kb):
