@@ -607,6 +607,18 @@ def test_tower_variants_agree_bit_for_bit(kb):
         p0, v0 = nets["0"].forward_full(batch)
         p2, v2 = plain.forward_full(batch)
         assert np.array_equal(p0, p2) and np.array_equal(v0, v2)
+    # the general issue loop (any layer shape, one wait per weight block; KB_TOWER_WAIT_GROUP=1) against the straight-line
+    # routines the 3x3 / 1x1 layers of this network take by default
+    os.environ["KB_TOWER_WAIT_GROUP"] = "1"
+    try:
+        general = kb.NN(64, 2)
+        general.load_blob(blob)
+    finally:
+        del os.environ["KB_TOWER_WAIT_GROUP"]
+    for batch in (obs[:7], obs, big):
+        p0, v0 = nets["0"].forward_full(batch)
+        p3, v3 = general.forward_full(batch)
+        assert np.array_equal(p0, p3) and np.array_equal(v0, v3)
     # pool step (legal-move mode): the trees the two kernels build must be identical.  With KB_TOWER_GATHER=1 k_tower64
     # computes the logits of the legal moves only, as fp32 dot products on the CUDA cores, instead of taking them from the
     # policyconv2 MMA (measured alternative, off by default): compared further down
