@@ -374,6 +374,14 @@ def test_net_vs_oracle(kb, F, R, B):
     _check_net(kb, F, R, B, seed=12)
 
 
+@pytest.mark.parametrize("R,B", [(0, 9), (3, 40), (6, 300)])
+def test_fused_tower_depths_vs_oracle(kb, R, B):
+    """The fused 64-filter kernel takes 0..6 residual blocks; the weight ring's position at the start of a layer (and so
+    the wrap-around of the straight-line issue routines) depends on the layer count, and 300 boards = 43 items: one CTA
+    per item here, two items per CTA on the 2048-board batch of the variants test."""
+    _check_net(kb, 64, R, B, seed=14)
+
+
 def test_net_fused_kernel_matches_per_layer_kernels(kb):
     """filters == 64 runs as ONE fused kernel (k_tower64); the per-layer kernels (k_conv + heads)
     must give the same network."""
