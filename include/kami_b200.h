@@ -162,6 +162,8 @@ int kb_tree_env(kb_pool* p, int tree, kb_position* out);           /* MCTS::get_
 /* batched phases over all trees of the pool (device-resident) */
 int kb_pool_select(kb_pool* p);                 /* every tree: one leaf (terminals absorbed, moves made at budget) */
 int kb_pool_leaf_positions(kb_pool* p, kb_position* out /*[n_trees] host*/);
+/* (a pinned policy array -- kb_host_alloc_pinned / kb_host_register -- is read in place: only the legal moves' entries
+ *  cross the link, mcts.h:273; a pageable one is copied in full) */
 int kb_pool_expand(kb_pool* p, const float* policy /*[n][4672] host*/, const float* value /*[n] host*/, int disable_bootstrap);
 int kb_pool_expand_dev(kb_pool* p, const float* policy_dev, const float* value_dev, int disable_bootstrap);
 /* compact forms of the same exchange: every pending leaf's Env::actions() list (row pitch 128, -1 padded) out;

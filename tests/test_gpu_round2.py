@@ -419,17 +419,25 @@ def test_hostio_forms_build_the_same_trees_as_the_resident_step(kb, dense):
 
 
 def test_leaf_actions_and_compact_expand(kb):
-    """kb_pool_leaf_actions + kb_pool_expand_compact == the dense kb_pool_expand on the same policy rows."""
+    """kb_pool_leaf_actions + kb_pool_expand_compact == the dense kb_pool_expand on the same policy rows, and the same with
+    the dense rows in a PINNED array, which kb_pool_expand reads in place (legal moves' entries only) instead of copying."""
+    import ctypes as C
+
     from kami_b200 import api
 
     n = 64
     kw = dict(noise_weight=0.0, **H.DEF_YML)
     a = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
     b = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
+    c = kb.TreePool(n, 1 << 13, _cfg(kb, **kw))
+    L, hp = kb.lib(), C.c_void_p()
+    api._ck(L.kb_host_alloc_pinned(C.byref(hp), n * H.PSIZE * 4))
+    pinned_pol = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(n * H.PSIZE,)).reshape(n, H.PSIZE)
     rng = np.random.RandomState(3)
     for it in range(30):
         a.select()
         b.select()
+        c.select()
         acts, cnt = b.leaf_actions()
         la, lc = api.legal_actions(b.leaf_positions())
         assert np.array_equal(cnt, lc)
@@ -443,8 +451,12 @@ def test_leaf_actions_and_compact_expand(kb):
             prior[t, :cnt[t]] = pol[t, acts[t, :cnt[t]]]
         a.expand(pol, val)
         b.expand_compact(prior, val)
+        pinned_pol[:] = pol
+        c.expand(pinned_pol, val)
     for t in range(n):
-        assert a.tree(t).digest() == b.tree(t).digest()
+        assert a.tree(t).digest() == b.tree(t).digest() == c.tree(t).digest()
+    del pinned_pol
+    L.kb_host_free_pinned(hp)
 
 
 def test_flush_trees(kb):
