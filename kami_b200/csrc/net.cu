@@ -748,8 +748,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_conv2(cons
 //   policy conv2 1x1: H -> fp32 logits (overlay), softmax over 4672 per board -> global.
 //
 // Warp roles: warp 0 bulk-TMA producer (input slab + all weight blocks in consumption order
-// through a 5-stage ring), warp 1 tcgen05.mma issuer, warp 2 TMEM allocator, warps 4-11
-// epilogue (two warps per TMEM lane quarter, splitting the accumulator columns).
+// through a 5-stage ring); warp 1 tcgen05.mma issuer -- ONE lane issues a whole layer as a straight
+// line of weight-stationary MMAs (tower_issue_3x3_n64 / tower_issue_1x1 below; the general loop
+// serves any other layer shape); warp 2 TMEM allocator, warps 2-3 the value head's Linear + tanh;
+// warps 4.. the EW epilogue warps (EW = 16: one M tile of a layer per warp and TMEM lane quarter;
+// EW = 8: two tiles per warp).
 // ------------------------------------------------------------------------------------------
 struct FusedLayer {
     int src_off, dst_off;  // byte offsets of the source / destination slabs inside the region
@@ -790,7 +793,9 @@ struct FusedParams {
     int gather;  // 1: in legal-move mode the logits of the legal moves are computed where they are needed, from the policy head's
                  //    features and policyconv2's rows in the weight ring, instead of all 4 672 by MMA (KB_TOWER_GATHER=1; measured
                  //    62.0 k vs 64.0 k cycles per item on young games, 69.9 vs 70.1 us per step on aged ones: off by default)
-    int wait_group;  // weight blocks the MMA warp waits for at a time, 1..FZ_NSTAGE (KB_TOWER_WAIT_GROUP, default 3)
+    int wait_group;  // 1: every layer through the general issue loop (one ring wait per weight block); otherwise the 3x3 / 1x1 layers
+                     //    of the standard network take the straight-line routines and the general loop waits for up to this many
+                     //    blocks at a time (KB_TOWER_WAIT_GROUP, default 3)
     FusedLayer layer[16];
 };
 #ifndef KB_TOWER_PIPE_DEFAULT
