@@ -277,6 +277,58 @@ KB_HD bool make_move(const Pos& cur, u16 mv, Pos& next) {
     return true;
 }
 
+// make_move<false, true>(cur, mv, next) + set_full_key(next) for the tree descent, written for LATENCY: every lane of
+// the warp runs this same scalar chain once per level (2.0 k of the 3.7 k cycles a level of the descent took), so what
+// counts is the length of the dependent chain, not the instruction count.  Source and destination are cleared from all
+// six boards at once and the arriving piece is or-ed into its board (independent per board) instead of three or four
+// toggles that each scan the types; the two type lookups are or-trees instead of six-deep select chains; the Zobrist
+// terms are requested together.  En passant, castling and promotions -- rare -- take the general routine.  Same fields
+// as make_move (tests/hostcore: differential test on every legal move of random games); `check` is left as in `cur`
+// like make_move<false> leaves it.
+KB_HD void descend_move(const Pos& cur, u16 mv, Pos& next) {
+    const int src = (mv >> 6) & 63, dst = mv & 63, promo = mv >> 12;
+    const u64 sb = bit(src), db = bit(dst);
+    const int us = cur.ctm;
+    int stype = 0, dtype = 0;
+    bool cap = false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        stype |= (cur.pc[i] & sb) ? i : 0;
+        dtype |= (cur.pc[i] & db) ? i : 0;
+        cap |= (cur.pc[i] & db) != 0;
+    }
+    const int df = (dst & 7) - (src & 7);
+    const bool special = (stype == PAWN && dst == cur.ep) || (stype == KING && (df > 1 || df < -1)) || promo < 12;
+    if (special) {
+        make_move<false, true>(cur, mv, next);
+        set_full_key(next);
+        return;
+    }
+    const u64 clr = ~(sb | db);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) next.pc[i] = (cur.pc[i] & clr) | (i == stype ? db : 0ULL);
+    next.white = (cur.white & clr) | (us == WHITE ? db : 0ULL);
+    u64 bk = cur.bkey ^ KB_ZK(src * 12 + stype * 2 + us) ^ KB_ZK(dst * 12 + stype * 2 + us);
+    if (cap) bk ^= KB_ZK(dst * 12 + dtype * 2 + (us ^ 1));
+    next.bkey = bk;
+    const u64 sd = sb | db;
+    int castle = cur.castle;
+    if (stype == KING) castle &= us == WHITE ? ~0x3 : ~0xC;
+    if (sd & (bit(4) | bit(7))) castle &= ~1;
+    if (sd & (bit(4) | bit(0))) castle &= ~2;
+    if (sd & (bit(60) | bit(63))) castle &= ~4;
+    if (sd & (bit(60) | bit(56))) castle &= ~8;
+    next.castle = (u8)castle;
+    const int dr = (dst >> 3) - (src >> 3);
+    next.ep = (stype == PAWN && (dr > 1 || dr < -1)) ? (u8)(dst + (us == WHITE ? -8 : 8)) : (u8)0xFF;
+    next.hmc = (stype == PAWN || cap) ? (u8)0 : (u8)(cur.hmc + 1);
+    next.ctm = (u8)(us ^ 1);
+    next.ply = (u16)(cur.ply + 1);
+    next.check = cur.check;
+    next.pad = cur.pad;
+    set_full_key(next);
+}
+
 // The return value of make_move<false>(p, mv, next) -- "the mover's king is safe afterwards" (position.c:316-319) --
 // without building `next`: the king's attackers are looked up in p's own bitboards under the occupancy the move leaves
 // behind (source emptied, destination filled, en-passant victim removed, castling rook relocated), with the captured

@@ -31,6 +31,25 @@ int hc_legality_diff(const void* pos80, int* tested) {
     *tested = l.n < MAX_MOVES ? l.n : MAX_MOVES;
     return bad;
 }
+// every legal action of the position: descend_move must produce make_move<false, true> + set_full_key byte for byte
+int hc_descend_diff(const void* pos80, int* tested) {
+    const Pos& p = *(const Pos*)pos80;
+    u16 acts[MAX_MOVES];
+    const int n = legal_actions_scalar(p, acts);
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+        Pos a, b;
+        memset(&a, 0, sizeof(a));
+        memset(&b, 0, sizeof(b));
+        const u16 mv = decode_action(p, acts[i]);
+        make_move<false, true>(p, mv, a);
+        set_full_key(a);
+        descend_move(p, mv, b);
+        if (memcmp(&a, &b, sizeof(Pos)) != 0) ++bad;
+    }
+    *tested = n;
+    return bad;
+}
 int hc_push(void* pos80, int action) {
     Pos cur = *(Pos*)pos80, nx;
     bool legal = make_move<true>(cur, decode_action(cur, action), nx);

@@ -53,6 +53,27 @@ def test_fast_legality_equals_make_move(hc):
     assert tested > 400000 and bad == 0, (tested, bad)
 
 
+def test_descent_move_equals_make_move(hc):
+    """descend_move (the latency-oriented position update of the tree descent, csrc/chess.cuh) == make_move<false, true> +
+    set_full_key, all 80 bytes, on every legal move of positions from seeded random games (captures, en passant, castling
+    with and without rights, promotions and the (Q3) queen-promotion quirk, double pushes all occur)."""
+    rng = random.Random(12)
+    tested = bad = 0
+    n = C.c_int()
+    for g in range(200):
+        pos = np.zeros(80, np.uint8)
+        hc.hc_start(vp(pos))
+        for ply in range(200):
+            bad += hc.hc_descend_diff(vp(pos), C.byref(n))
+            tested += n.value
+            buf = np.zeros(128, np.int32)
+            k = hc.hc_legal_actions(vp(pos), buf.ctypes.data_as(C.POINTER(C.c_int)))
+            if k == 0:
+                break
+            hc.hc_push(vp(pos), int(buf[rng.randrange(k)]))
+    assert tested > 400000 and bad == 0, (tested, bad)
+
+
 def test_device_core_matches_oracle(hc):
     rng = random.Random(5)
     npos = 0
