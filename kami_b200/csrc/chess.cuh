@@ -567,6 +567,38 @@ KB_HD int encode_action(const Pos& p, u16 mv) {
     else base = df > 0 ? 42 : 49;
     return 73 * src + base + dist;
 }
+// decode_action by table (the tree descent's copy: one uniform constant load instead of two divisions and three select
+// chains on the critical path of every level): entry t = move type 0..72, low byte = destination - source (white's view),
+// high byte = promotion piece or 0xF.  tests/hostcore checks it against decode_action on all 4 672 actions, both sides.
+#if defined(__CUDACC__)
+#define KB_CTAB static __constant__ const
+#else
+#define KB_CTAB static const
+#endif
+#define KB_MT(d, p) (short)((((p) & 0xF) << 8) | ((d) & 0xFF))
+KB_CTAB short kb_move_type[73] = {
+    KB_MT(8, 15),   KB_MT(16, 15),  KB_MT(24, 15),  KB_MT(32, 15),  KB_MT(40, 15),  KB_MT(48, 15),  KB_MT(56, 15),   // N
+    KB_MT(-8, 15),  KB_MT(-16, 15), KB_MT(-24, 15), KB_MT(-32, 15), KB_MT(-40, 15), KB_MT(-48, 15), KB_MT(-56, 15),  // S
+    KB_MT(1, 15),   KB_MT(2, 15),   KB_MT(3, 15),   KB_MT(4, 15),   KB_MT(5, 15),   KB_MT(6, 15),   KB_MT(7, 15),    // E
+    KB_MT(-1, 15),  KB_MT(-2, 15),  KB_MT(-3, 15),  KB_MT(-4, 15),  KB_MT(-5, 15),  KB_MT(-6, 15),  KB_MT(-7, 15),   // W
+    KB_MT(9, 15),   KB_MT(18, 15),  KB_MT(27, 15),  KB_MT(36, 15),  KB_MT(45, 15),  KB_MT(54, 15),  KB_MT(63, 15),   // NE
+    KB_MT(7, 15),   KB_MT(14, 15),  KB_MT(21, 15),  KB_MT(28, 15),  KB_MT(35, 15),  KB_MT(42, 15),  KB_MT(49, 15),   // NW
+    KB_MT(-7, 15),  KB_MT(-14, 15), KB_MT(-21, 15), KB_MT(-28, 15), KB_MT(-35, 15), KB_MT(-42, 15), KB_MT(-49, 15),  // SE
+    KB_MT(-9, 15),  KB_MT(-18, 15), KB_MT(-27, 15), KB_MT(-36, 15), KB_MT(-45, 15), KB_MT(-54, 15), KB_MT(-63, 15),  // SW
+    KB_MT(6, 15),   KB_MT(15, 15),  KB_MT(10, 15),  KB_MT(17, 15),  KB_MT(-10, 15), KB_MT(-17, 15), KB_MT(-6, 15), KB_MT(-15, 15),  // knight
+    KB_MT(7, KNIGHT), KB_MT(8, KNIGHT), KB_MT(9, KNIGHT), KB_MT(7, BISHOP), KB_MT(8, BISHOP), KB_MT(9, BISHOP),
+    KB_MT(7, ROOK),   KB_MT(8, ROOK),   KB_MT(9, ROOK)};  // underpromotions
+#undef KB_MT
+KB_HD u16 decode_action_tab(const Pos& p, int action) {
+    int src = action / 73;
+    const int e = kb_move_type[action - src * 73];
+    int dst = src + (int)(signed char)(e & 0xFF);
+    if (p.ctm == BLACK) {
+        src = 63 - src;
+        dst = 63 - dst;
+    }
+    return (u16)(((src & 63) << 6) | (dst & 63) | ((e >> 8) << 12));
+}
 KB_HD u16 decode_action(const Pos& p, int action) {
     int src = action / 73, t = action % 73, dst, promo = 0xF;
     if (t < 56) {

@@ -50,6 +50,13 @@ int hc_descend_diff(const void* pos80, int* tested) {
     *tested = n;
     return bad;
 }
+// decode_action_tab against decode_action on every action code, for the side to move of the given position
+int hc_decode_tab_diff(const void* pos80) {
+    const Pos& p = *(const Pos*)pos80;
+    int bad = 0;
+    for (int a = 0; a < 4672; ++a) bad += decode_action(p, a) != decode_action_tab(p, a);
+    return bad;
+}
 int hc_push(void* pos80, int action) {
     Pos cur = *(Pos*)pos80, nx;
     bool legal = make_move<true>(cur, decode_action(cur, action), nx);

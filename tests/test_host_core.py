@@ -72,6 +72,14 @@ def test_descent_move_equals_make_move(hc):
                 break
             hc.hc_push(vp(pos), int(buf[rng.randrange(k)]))
     assert tested > 400000 and bad == 0, (tested, bad)
+    # and the table form of decode_action the descent uses: all 4 672 action codes, white and black to move
+    pos = np.zeros(80, np.uint8)
+    hc.hc_start(vp(pos))
+    assert hc.hc_decode_tab_diff(vp(pos)) == 0
+    buf = np.zeros(128, np.int32)
+    hc.hc_legal_actions(vp(pos), buf.ctypes.data_as(C.POINTER(C.c_int)))
+    hc.hc_push(vp(pos), int(buf[0]))
+    assert hc.hc_decode_tab_diff(vp(pos)) == 0
 
 
 def test_device_core_matches_oracle(hc):
